@@ -1,0 +1,119 @@
+"""Pins the oracle (oracle/net.py, decode.py, nms.py) against outputs of the REFERENCE'S OWN code
+(tests/golden/*.npz, produced by tests/golden/gen_golden.py from /root/reference on the numpy TF stand-in)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as GI
+from byolo import priors as P
+from byolo import weights as W
+from oracle import decode as D
+from oracle import net as ON
+from oracle import nms as ONMS
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+PRI = P.as_scale_list(P.by_stride('ECP_9_PRIORS'))
+OBJ = {'standard': 4, 'aleatoric': 9, 'epistemic': 14}
+
+
+def _close(a, b, rtol, atol, what):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    err = np.abs(a - b) - (atol + rtol * np.abs(b))
+    assert np.all((err <= 0) | (np.isnan(a) & np.isnan(b))), '%s: worst excess %g at %s' % (
+        what, np.nanmax(err), np.unravel_index(np.nanargmax(err), err.shape))
+
+
+@pytest.fixture(scope='module')
+def runs():
+    out = {}
+    for name, case in GI.CASES.items():
+        w = W.synthetic(case['variant'], case['cls_cnt'], case['weight_seed'])
+        fwd = ON.Forward(case['variant'], w, case['cls_cnt'], torch.float32, keep_layers=True)
+        out[name] = fwd.run(GI.images(case), T=case.get('T'), seed=case.get('dropout_seed', 0))
+    return out
+
+
+def test_prior_tables_match_reference():
+    g = np.load(os.path.join(G, 'priors.npz'))
+    for n in P.NAMES:
+        mine = np.array([p for s in P.as_scale_list(P.by_stride(n)) for p in s])
+        assert np.array_equal(mine, g[n]), n
+
+
+def test_decode_matches_reference_numpy_implementation():
+    """lib_yolo/utils.py:72-123 is the one non-TF statement of the aleatoric decode in the reference."""
+    g = np.load(os.path.join(G, 'utils_numpy_decode.npz'))
+    pri = [tuple(p) for p in g['priors']]
+    rows = D.decode_aleatoric(g['pred'], pri, 0)                       # [S, 3*g*g, 16] prior-major
+    S, lh, lw, _ = g['pred'].shape
+    mine = rows.reshape(S, 3, lh, lw, 16).transpose(0, 2, 3, 1, 4).reshape(S, lh * lw * 3, 16)   # cell-major like utils
+    ref = g['boxes']      # [y0,x0,y1,x1, var*4, obj, obj_stddev, cls*2, cls_stddev*2]
+    _close(mine[..., 0:8], ref[..., 0:8], 2e-6, 1e-7, 'box+var')
+    _close(mine[..., 9], ref[..., 8], 2e-6, 1e-7, 'obj')
+    _close(mine[..., 11:13], ref[..., 10:12], 2e-6, 1e-7, 'cls')
+
+
+@pytest.mark.parametrize('name', list(GI.CASES))
+def test_forward_matches_reference_graph(name, runs):
+    case, g = GI.CASES[name], np.load(os.path.join(G, name + '.npz'))
+    res = runs[name]
+    last = res[-1]
+    # backbone taps (independent conv implementations: torch/oneDNN here, numpy im2col+sgemm in the shim)
+    _close(last['layers'][74][-g['dn_out'].shape[0]:], g['dn_out'], 1e-4, 1e-4, 'dn_out')
+    _close(last['layers'][36][-g['l36'].shape[0]:, ::4, ::4, ::8], g['l36'], 1e-4, 1e-4, 'l36')
+    _close(last['layers'][61][-g['l61'].shape[0]:, ::2, ::2, ::8], g['l61'], 1e-4, 1e-4, 'l61')
+    for j in range(3):
+        mine = np.stack([r['raw'][j] for r in res]) if case['variant'] == 'epistemic' else res[0]['raw'][j]
+        _close(mine, g['raw%d' % j], 1e-4, 2e-4, 'raw%d' % j)
+
+
+@pytest.mark.parametrize('name', list(GI.CASES))
+def test_decode_rows_match_reference_graph(name):
+    """Decode fed with the reference's raw head outputs: isolates decode.py + concat order."""
+    case, g = GI.CASES[name], np.load(os.path.join(G, name + '.npz'))
+    v = case['variant']
+    if v == 'epistemic':
+        rows = np.stack([D.rows_from_raw(v, [g['raw%d' % j][b] for j in range(3)], PRI) for b in range(case['batch'])])
+        # cancellation columns (covariance diag 4:8, det 12, MI 15/19): absolute floors, see DESIGN.md
+        atol = np.full(23, 1e-6)
+        atol[4:8] = 2e-5
+        atol[12] = 1e-7
+        atol[[15, 19]] = 2e-6
+        _close(rows, g['rows'], 1e-4, atol, 'rows')
+        rows64 = np.stack([D.rows_from_raw(v, [g['raw%d' % j][b].astype(np.float64) for j in range(3)], PRI,
+                                           dtype=np.float64) for b in range(case['batch'])])
+        a64 = np.full(23, 1e-5)
+        a64[12] = 1e-6
+        _close(rows64, g['rows64'], 2e-3, a64, 'rows64')       # raw inputs are the fp32 run's; fp64 run differs slightly
+    else:
+        rows = D.rows_from_raw(v, [g['raw%d' % j] for j in range(3)], PRI)
+        _close(rows, g['rows'], 1e-5, 1e-6, 'rows')
+
+
+@pytest.mark.parametrize('name', list(GI.CASES))
+def test_nms_matches_reference_graph_bit_exact(name):
+    """NMS fed with the reference's rows: selection and gathered rows must be identical."""
+    case, g = GI.CASES[name], np.load(os.path.join(G, name + '.npz'))
+    for b in range(case['batch']):
+        got, idx = ONMS.nms_gather(g['rows'][b], OBJ[case['variant']])
+        n = int(g['nms_count'][b])
+        assert len(idx) == n
+        assert np.array_equal(got, g['nms_rows'][b, :n])
+        assert np.array_equal(idx, ONMS.nms_numpy(g['rows'][b], OBJ[case['variant']]))
+
+
+def test_nms_ties_and_degenerate_boxes():
+    rng = np.random.default_rng(3)
+    n = 400
+    c = rng.uniform(0, 1, (n, 2))
+    s = rng.uniform(0.02, 0.3, (n, 2))
+    rows = np.concatenate([c - s / 2, c + s / 2, rng.uniform(0, 1, (n, 1))], 1).astype(np.float32)
+    rows[50:100, 4] = rows[0:50, 4]            # exact score ties -> lower index first
+    rows[10, 2:4] = rows[10, 0:2]              # zero-area box: IoU 0 with everything, always selected
+    rows[11, [0, 2]] = rows[11, [2, 0]]        # flipped corners are re-ordered by min/max
+    a, b = ONMS.nms(rows, 4, 1000), ONMS.nms_numpy(rows, 4, 1000)
+    assert np.array_equal(a, b) and 10 in a
+    assert len(ONMS.nms(rows[:0], 4)) == 0
+    assert len(ONMS.nms(rows, 4, max_out=7)) == 7

@@ -1,0 +1,163 @@
+"""Python face of libbyolo: an `Engine` owns one C handle; torch CUDA tensors are only the buffer type
+(data_ptr() in, data_ptr() out) - no torch op runs on the hot path."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, priors as _priors, weights as _weights
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Engine:
+    """variant: 'standard' | 'aleatoric' | 'epistemic'; priors: {32,16,8: [Prior]*3} as in the reference config."""
+
+    def __init__(self, variant, img_hw, cls_cnt=2, priors=None, T=1, max_batch=16, precision='fp16', drop_prob=0.1,
+                 standard_test_dropout=False, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('byolo needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.lib = _lib.lib()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        torch.cuda.set_device(self.device)
+        torch.cuda.current_stream().synchronize()       # makes sure the primary context exists
+        self.variant, self.cls_cnt, self.T = variant, cls_cnt, (T if variant == 'epistemic' else 1)
+        self.H, self.W = int(img_hw[0]), int(img_hw[1])
+        pri = _priors.as_scale_list(priors if priors is not None else _priors.by_stride('ECP_9_PRIORS'))
+        cfg = _lib.Config(variant=_lib.VARIANT_ID[variant], height=self.H, width=self.W, cls_cnt=cls_cnt,
+                          max_batch=max_batch, T=self.T, precision=_lib.PRECISION_ID[precision],
+                          standard_test_dropout=int(bool(standard_test_dropout)), drop_prob=drop_prob)
+        flat = [p for scale in pri for p in scale]
+        for i, (h, w) in enumerate(flat):
+            cfg.prior_h[i], cfg.prior_w[i] = h, w
+        self.h = C.c_void_p()
+        _lib.check(self.lib.byolo_create(C.byref(cfg), C.byref(self.h)))
+        n, d, o, c = (C.c_int32() for _ in range(4))
+        _lib.check(self.lib.byolo_output_shape(self.h, C.byref(n), C.byref(d), C.byref(o), C.byref(c)))
+        self.N, self.D, self.obj_idx, self.cls_start_idx = n.value, d.value, o.value, c.value
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h.value:
+            self.lib.byolo_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------- weights
+    def load_weights(self, weights):
+        """weights: list of 75 dicts (byolo.weights) or an already packed BYW1 blob."""
+        blob = weights if isinstance(weights, (bytes, bytearray)) else _weights.pack(self.variant, weights, self.cls_cnt)
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        _lib.check(self.lib.byolo_load_weights(self.h, C.cast(buf, C.c_void_p), len(blob)))
+        return self
+
+    # ------------------------------------------------------------------------------------------- hot path
+    def _check_img(self, img):
+        assert img.is_cuda and img.dtype == torch.float32 and img.is_contiguous()
+        assert tuple(img.shape[1:]) == (self.H, self.W, 3), img.shape
+        return img.shape[0]
+
+    def forward(self, img, seed=0, image_index0=0, out=None):
+        """img [B,H,W,3] fp32 cuda in [0,1) -> rows [B,N,D] (concat_bbox order)."""
+        B = self._check_img(img)
+        rows = out if out is not None else torch.empty((B, self.N, self.D), dtype=torch.float32, device=img.device)
+        _lib.check(self.lib.byolo_forward(self.h, _ptr(img), B, seed, image_index0, _ptr(rows), _stream()))
+        return rows
+
+    def detect(self, img, seed=0, image_index0=0, max_out=1000, iou_thr=0.5, want_rows=False):
+        """-> (boxes [B,max_out,D] selection order zero padded, count [B] int32, idx [B,max_out] int32[, rows])."""
+        B = self._check_img(img)
+        dev = img.device
+        boxes = torch.empty((B, max_out, self.D), dtype=torch.float32, device=dev)
+        idx = torch.empty((B, max_out), dtype=torch.int32, device=dev)
+        cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+        rows = torch.empty((B, self.N, self.D), dtype=torch.float32, device=dev) if want_rows else None
+        _lib.check(self.lib.byolo_detect(self.h, _ptr(img), B, seed, image_index0, iou_thr, max_out, _ptr(rows),
+                                         _ptr(boxes), _ptr(idx), _ptr(cnt), _stream()))
+        return (boxes, cnt, idx, rows) if want_rows else (boxes, cnt, idx)
+
+    def detect_host(self, img_host, seed=0, image_index0=0, max_out=1000, iou_thr=0.5, out=None):
+        """Host numpy/pinned-tensor images in, host numpy results out (copies + sync inside): the sess.run analogue."""
+        a = img_host.numpy() if isinstance(img_host, torch.Tensor) else np.ascontiguousarray(img_host, np.float32)
+        assert a.dtype == np.float32 and a.shape[1:] == (self.H, self.W, 3)
+        B = a.shape[0]
+        if out is None:
+            out = (np.empty((B, max_out, self.D), np.float32), np.empty((B,), np.int32))
+        _lib.check(self.lib.byolo_detect_host(self.h, _np_ptr(a), B, seed, image_index0, iou_thr, max_out,
+                                              _np_ptr(out[0]), _np_ptr(out[1]), _stream()))
+        return out
+
+    def decode(self, raws, B):
+        """raws: three dense fp32 cuda tensors [B*T,g,g,ch] -> rows [B,N,D]."""
+        rows = torch.empty((B, self.N, self.D), dtype=torch.float32, device=raws[0].device)
+        _lib.check(self.lib.byolo_decode(self.h, _ptr(raws[0]), _ptr(raws[1]), _ptr(raws[2]), B, _ptr(rows), _stream()))
+        return rows
+
+    def activation(self, conv_index):
+        """Dense fp32 [S,H,W,C] copy of the output of conv `conv_index` (0..74) of the last forward."""
+        shape = (C.c_int32 * 4)()
+        cap = 1 << 28
+        # query shape first with a tiny call is not possible without capacity; allocate by known upper bound lazily
+        probe = torch.empty((1,), dtype=torch.float32, device=self.device)
+        rc = self.lib.byolo_get_activation(self.h, conv_index, _ptr(probe), 0, C.byref(shape), _stream())
+        n = int(shape[0]) * int(shape[1]) * int(shape[2]) * int(shape[3])
+        assert rc < 0 and n > 0 and n <= cap, (rc, list(shape))
+        dst = torch.empty(tuple(int(s) for s in shape), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.byolo_get_activation(self.h, conv_index, _ptr(dst), n, C.byref(shape), _stream()))
+        return dst
+
+    def launch_count(self, B):
+        return _lib.check(self.lib.byolo_launch_count(self.h, B))
+
+    def flops_per_image(self):
+        return float(self.lib.byolo_flops_per_image(self.h))
+
+
+def nms(rows, obj_idx, max_out=1000, iou_thr=0.5):
+    """rows [B,N,D] fp32 cuda -> (boxes [B,max_out,D], count [B], idx [B,max_out])."""
+    assert rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous() and rows.dim() == 3
+    B, N, D = rows.shape
+    boxes = torch.empty((B, max_out, D), dtype=torch.float32, device=rows.device)
+    idx = torch.empty((B, max_out), dtype=torch.int32, device=rows.device)
+    cnt = torch.zeros((B,), dtype=torch.int32, device=rows.device)
+    with torch.cuda.device(rows.device):
+        _lib.check(_lib.lib().byolo_nms(_ptr(rows), B, N, D, obj_idx, iou_thr, max_out, _ptr(boxes), _ptr(idx), _ptr(cnt),
+                                        _stream()))
+    return boxes, cnt, idx
+
+
+def conv_layer(x, kernel, bn=None, bias=None, x2=None, residual=None, stride=1, upsample=False, precision='fp16',
+               dropout_layer=-1, T=1, seed=0, image_index0=0, drop_prob=0.1):
+    """Per-layer test hook (byolo_conv_layer): x [S,H,W,C1] (+ x2 [S,H,W,C2]) dense fp32 cuda; kernel HWIO numpy;
+    bn = dict(beta,gamma,mean,var) or bias array.  Returns dense fp32 [S,Ho,Wo,cout] (x2 size if upsample)."""
+    S, H, W, c1 = x.shape
+    c2 = x2.shape[3] if x2 is not None else 0
+    k = kernel.shape[0]
+    cout = kernel.shape[3]
+    kern = np.ascontiguousarray(kernel, np.float32)
+    bn_a = np.ascontiguousarray(np.concatenate([bn[n] for n in ('beta', 'gamma', 'mean', 'var')]), np.float32) \
+        if bn is not None else None
+    bias_a = np.ascontiguousarray(bias, np.float32) if bias is not None else None
+    Ho, Wo = H // stride, W // stride
+    out = torch.empty((S, 2 * Ho if upsample else Ho, 2 * Wo if upsample else Wo, cout), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().byolo_conv_layer(
+            _lib.PRECISION_ID[precision], _ptr(x.contiguous()), _ptr(x2.contiguous() if x2 is not None else None), S, H, W,
+            c1, c2, k, stride, cout, _np_ptr(kern), _np_ptr(bn_a), _np_ptr(bias_a),
+            _ptr(residual.contiguous() if residual is not None else None), int(upsample), dropout_layer, T, seed,
+            image_index0, drop_prob, _ptr(out), _stream()))
+    return out

@@ -1,0 +1,223 @@
+// CUDA-core kernels: the exact fp32 conv path (precision modes "fp32" / "fp16-simt", used to cross-check the
+// tensor-core kernel layer by layer and to give bit-stable rows to the NMS end-to-end tests), the 3-channel stem
+// conv (K1b), the MC-sample stacking copy, and dense <-> padded-NHWC repacking for the test hooks.
+// Same semantics as conv_umma.cu: conv -> [dropout] -> + BN shift -> leaky -> [+ residual]
+// (/root/reference/lib_yolo/layers.py:545-575, :505-507, :521-524).
+#include "common.cuh"
+
+namespace byolo {
+
+template <typename T> __device__ __forceinline__ float ld_act(const T* p);
+template <> __device__ __forceinline__ float ld_act<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_act<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <typename T> __device__ __forceinline__ void st_act(T* p, float v);
+template <> __device__ __forceinline__ void st_act<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_act<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+// one thread = one output pixel x 4 consecutive output channels
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const T* __restrict__ in1, const T* __restrict__ in2, Geom g, int c2, int k, int stride, int cout_pad,
+                 const float* __restrict__ w /*[K, cout_pad]*/, Epilogue ep, long long total) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int groups = cout_pad >> 2;
+    const int cg = (int)(gid % groups);
+    const long long pix = gid / groups;
+    const int Ho = g.H / stride, Wo = g.W / stride;
+    const int x = (int)(pix % Wo);
+    const int y = (int)((pix / Wo) % Ho);
+    const int s = (int)(pix / ((long long)Wo * Ho));
+    const int c = cg * 4;
+    const int C1 = g.C;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int kk = 0;
+    for (int r = 0; r < k; ++r)
+        for (int q = 0; q < k; ++q) {
+            const int py = (k == 3) ? y * stride + r : y + 1;
+            const int px = (k == 3) ? x * stride + q : x + 1;
+            const long long prow = ((long long)s * g.PH() + py) * g.PW() + px;
+            const T* a1 = in1 + prow * C1;
+            for (int ci = 0; ci < C1; ++ci, ++kk) {
+                const float a = ld_act<T>(a1 + ci);
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)kk * cout_pad + c));
+                acc[0] = fmaf(a, wv.x, acc[0]);
+                acc[1] = fmaf(a, wv.y, acc[1]);
+                acc[2] = fmaf(a, wv.z, acc[2]);
+                acc[3] = fmaf(a, wv.w, acc[3]);
+            }
+            if (in2) {
+                const T* a2 = in2 + prow * c2;
+                for (int ci = 0; ci < c2; ++ci, ++kk) {
+                    const float a = ld_act<T>(a2 + ci);
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)kk * cout_pad + c));
+                    acc[0] = fmaf(a, wv.x, acc[0]);
+                    acc[1] = fmaf(a, wv.y, acc[1]);
+                    acc[2] = fmaf(a, wv.z, acc[2]);
+                    acc[3] = fmaf(a, wv.w, acc[3]);
+                }
+            }
+        }
+    if (c >= ep.cout) return;
+    if (ep.drop.enabled) {
+        float v8[8];
+        const int c8 = c & ~7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v8[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v8[(c - c8) + j] = acc[j];
+        const uint32_t e = (uint32_t)(y * Wo + x) * (uint32_t)ep.cout + (uint32_t)c8;
+        dropout8(v8, ep.drop, e >> 3, s % ep.drop.T, ep.drop.image0 + s / ep.drop.T);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = v8[(c - c8) + j];
+    }
+    const long long opix = ((long long)s * (Ho + 2) + (y + 1)) * (Wo + 2) + (x + 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (c + j >= ep.cout) break;
+        float v = acc[j] + __ldg(ep.bias + c + j);
+        if (ep.leaky) v = fmaxf(v, 0.1f * v);
+        if (ep.out_mode == OUT_DENSE_F32) {
+            reinterpret_cast<float*>(ep.out)[((long long)(s * Ho + y) * Wo + x) * ep.ldc + c + j] = v;
+            continue;
+        }
+        if (ep.residual) v += ld_act<T>(reinterpret_cast<const T*>(ep.residual) + opix * ep.ldc + c + j);
+        T* ob = reinterpret_cast<T*>(ep.out);
+        if (ep.out_mode == OUT_PADDED) {
+            st_act<T>(ob + opix * ep.ldc + c + j, v);
+        } else {
+            for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx) {
+                    const long long qq = ((long long)s * (2 * Ho + 2) + (2 * y + dy + 1)) * (2 * Wo + 2) + (2 * x + dx + 1);
+                    st_act<T>(ob + qq * ep.ldc + c + j, v);
+                }
+        }
+    }
+}
+
+int launch_conv_simt(const ConvProblem& p, bool act_half, cudaStream_t st) {
+    BY_REQUIRE(p.cout_pad % 4 == 0, "cout_pad % 4");
+    const int Ho = p.gin.H / p.stride, Wo = p.gin.W / p.stride;
+    const long long total = (long long)p.gin.S * Ho * Wo * (p.cout_pad / 4);
+    const int grid = (int)((total + 255) / 256);
+    if (act_half)
+        conv_simt_kernel<__half><<<grid, 256, 0, st>>>((const __half*)p.in1, (const __half*)p.in2, p.gin, p.c2, p.k,
+                                                       p.stride, p.cout_pad, p.w32, p.ep, total);
+    else
+        conv_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)p.in1, (const float*)p.in2, p.gin, p.c2, p.k, p.stride,
+                                                      p.cout_pad, p.w32, p.ep, total);
+    BY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1b: stem conv 3 -> 32, 3x3 stride 1 SAME (darknet.py:10), reading the fp32 image [B,H,W,3] in [0,1) directly
+// (dataset_utils.py:6-11).  K = 27 is too shallow for the tensor pipe; the layer is bound by its 32-channel output.
+// One thread per output pixel: 27 inputs in registers, weights broadcast from shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+stem_kernel(const float* __restrict__ img, int B, int H, int W, const float* __restrict__ w, const float* __restrict__ bias,
+            T* __restrict__ out) {
+    __shared__ float sw[27 * 32];
+    __shared__ float sb[32];
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
+    if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long long)B * H * W) return;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+    float in[27];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int iy = y + r - 1, ix = x + q - 1;
+            const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+            const float* p = img + (((long long)b * H + iy) * W + ix) * 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) in[(r * 3 + q) * 3 + ch] = ok ? __ldg(p + ch) : 0.f;
+        }
+    T* o = out + (((long long)b * (H + 2) + y + 1) * (W + 2) + x + 1) * 32;
+#pragma unroll 4
+    for (int c = 0; c < 32; ++c) {
+        float a = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 27; ++kk) a = fmaf(in[kk], sw[kk * 32 + c], a);
+        a += sb[c];
+        st_act<T>(o + c, fmaxf(a, 0.1f * a));
+    }
+}
+
+int launch_stem(const float* img, int B, int H, int W, const float* w32, const float* bias, void* out, bool act_half,
+                cudaStream_t st) {
+    const long long total = (long long)B * H * W;
+    const int grid = (int)((total + 127) / 128);
+    if (act_half)
+        stem_kernel<__half><<<grid, 128, 0, st>>>(img, B, H, W, w32, bias, (__half*)out);
+    else
+        stem_kernel<float><<<grid, 128, 0, st>>>(img, B, H, W, w32, bias, (float*)out);
+    BY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// stack_feature_map (layers.py:595-597): dst[b*T + t] = src[b] for t < T.   plane_bytes % 16 == 0.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void stack_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long plane_v, int T, long long total_v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_v; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / plane_v, off = i - b * plane_v;
+        const uint4 v = __ldg(src + i);
+        for (int t = 0; t < T; ++t) dst[(b * T + t) * plane_v + off] = v;
+    }
+}
+
+int launch_stack(const void* src, void* dst, long long plane_bytes, int B, int T, cudaStream_t st) {
+    BY_REQUIRE(plane_bytes % 16 == 0, "plane size must be a multiple of 16 bytes");
+    const long long plane_v = plane_bytes / 16, total = plane_v * B;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    stack_kernel<<<grid, 256, 0, st>>>((const uint4*)src, (uint4*)dst, plane_v, T, total);
+    BY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// dense fp32 [S,H,W,C]  <->  padded T [S,H+2,W+2,C]   (test hooks / activation read-back only)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_kernel(const float* __restrict__ dense, T* __restrict__ padded, Geom g, long long total, int to_padded) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % g.C);
+        const long long pix = i / g.C;
+        const int x = (int)(pix % g.W), y = (int)((pix / g.W) % g.H), s = (int)(pix / ((long long)g.W * g.H));
+        const long long pi = (((long long)s * g.PH() + y + 1) * g.PW() + x + 1) * g.C + c;
+        if (to_padded)
+            st_act<T>(padded + pi, dense[i]);
+        else
+            const_cast<float*>(dense)[i] = ld_act<T>(padded + pi);
+    }
+}
+
+int launch_pack(const float* dense, void* padded, Geom g, bool act_half, cudaStream_t st) {
+    const long long total = (long long)g.S * g.H * g.W * g.C;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    if (act_half)
+        pack_kernel<__half><<<grid, 256, 0, st>>>(dense, (__half*)padded, g, total, 1);
+    else
+        pack_kernel<float><<<grid, 256, 0, st>>>(dense, (float*)padded, g, total, 1);
+    BY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_unpack(const void* padded, float* dense, Geom g, bool act_half, cudaStream_t st) {
+    const long long total = (long long)g.S * g.H * g.W * g.C;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    if (act_half)
+        pack_kernel<__half><<<grid, 256, 0, st>>>(dense, (__half*)const_cast<void*>(padded), g, total, 0);
+    else
+        pack_kernel<float><<<grid, 256, 0, st>>>(dense, (float*)const_cast<void*>(padded), g, total, 0);
+    BY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace byolo

@@ -1,0 +1,472 @@
+// K1: fused conv(1x1 | 3x3, stride 1 | 2) [+ dropout] + BN-shift + LeakyReLU [+ residual] as an implicit GEMM on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands staged by TMA into 128B/64B-swizzled
+// shared memory.  Replaces the Conv2D + FusedBatchNorm + LeakyRelu (+ RandomUniform/Floor/Mul dropout, + Add) node
+// groups that /root/reference/lib_yolo/layers.py:545-575 (conv), :505-507 (residual), :521-524 (dropout) create.
+//
+// GEMM view:  D[M = pixels, N = cout] = A[M, K] * W[N, K]^T,  K = taps * (C1 + C2), fp16 operands, fp32 accumulate.
+//   * stride 1: activations live in the padded-NHWC layout (common.cuh), so the A tile of filter tap (r,s) is the
+//     2D box rows [m0 + (r-1)*(W+2) + (s-1), +128) x channels [c0, c0+BK) of the flattened [rows, C] matrix: one
+//     plain 2D TMA load, no im2col buffer.  Border rows of the output are never stored (they stay zero).
+//   * stride 2 (5 darknet downsample layers, layers.py:616-635): the M tile is a BW x BH x BI patch of output
+//     pixels, loaded with a 4D TMA box over [C, W+2, H+2, S] with element strides (1,2,2,1).
+//   * a 1x1 conv over a channel concat [in1, in2] (route, layers.py:583-592) reads its K range from two maps.
+//
+// Structure: persistent CTAs (one per SM), 256 threads = warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-7 epilogue (TMEM lane quadrant = warp % 4); smem ring of `num_stages` {A,B} tiles with
+// full/empty mbarriers; two TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_umma.cuh"
+
+namespace byolo {
+
+// --------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (tcgen05 "smem descriptor"): start address, stride between 8-row
+// groups (SBO), version 1, swizzle mode.  The leading-dimension offset is unused for swizzled K-major tiles.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+constexpr int kThreads = 256;
+constexpr int kTileM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;
+
+struct SmemCtl {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
+                 const __grid_constant__ CUtensorMap map_b, const UmmaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // ring of {A,B} tiles, 1024B aligned (SWIZZLE_128B atoms are 1024B); control block behind it
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (ring - smem_u32(smem_raw)) + (size_t)p.num_stages * stage_bytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_kb = p.taps * (p.kb1 + p.kb2);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_a2);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.num_stages; ++s) {
+            mbar_init(smem_u32(&ctl->full[s]), 1);
+            mbar_init(smem_u32(&ctl->empty[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&ctl->acc_full[s]), 1);
+            mbar_init(smem_u32(&ctl->acc_empty[s]), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.num_n_tiles;
+                const int n0 = (tile % p.num_n_tiles) * p.BN;
+                int m0 = m_tile * kTileM, tx = 0, ty = 0, bi = 0;
+                if (p.s2) {
+                    tx = m_tile % p.tiles_x;
+                    ty = (m_tile / p.tiles_x) % p.tiles_y;
+                    bi = m_tile / (p.tiles_x * p.tiles_y);
+                }
+                int tap = 0, cb = 0;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t stage = it % p.num_stages, phase = (it / p.num_stages) & 1;
+                    mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1);
+                    const uint32_t full = smem_u32(&ctl->full[stage]);
+                    const uint32_t sa = ring + stage * stage_bytes, sb = sa + p.a_bytes;
+                    mbar_expect_tx(full, stage_bytes);
+                    const int r = tap / 3, s = tap - 3 * r;
+                    if (p.s2) {
+                        tma_load_4d(sa, &map_a1, full, cb * p.BK, 2 * tx * p.BW + s, 2 * ty * p.BH + r, bi * p.BI);
+                    } else if (cb < p.kb1) {
+                        const int shift = (p.taps == 9) ? (r - 1) * p.in_PW + (s - 1) : 0;
+                        tma_load_2d(sa, &map_a1, full, cb * p.BK, m0 + shift);
+                    } else {
+                        tma_load_2d(sa, &map_a2, full, (cb - p.kb1) * p.BK, m0);
+                    }
+                    tma_load_2d(sb, &map_b, full, kb * p.BK, n0);
+                    if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            uint32_t it = 0, tile_it = 0;
+            const int mma_per_kb = p.BK / 16;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
+                const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
+                mbar_wait(smem_u32(&ctl->acc_empty[as]), aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * kAccStride;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t stage = it % p.num_stages, phase = (it / p.num_stages) & 1;
+                    mbar_wait(smem_u32(&ctl->full[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t sa = ring + stage * stage_bytes, sb = sa + p.a_bytes;
+                    const uint64_t adesc = make_smem_desc(sa, p.sbo_bytes, p.layout_type);
+                    const uint64_t bdesc = make_smem_desc(sb, p.sbo_bytes, p.layout_type);
+                    for (int k = 0; k < mma_per_kb; ++k) {
+                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
+                    }
+                    umma_commit(smem_u32(&ctl->empty[stage]));       // frees the smem slot once these MMAs retire
+                }
+                umma_commit(smem_u32(&ctl->acc_full[as]));           // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
+        const Epilogue& ep = p.ep;
+        const int Ho = p.gout.H, Wo = p.gout.W;
+        uint32_t tile_it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
+            const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
+            const int m_tile = tile / p.num_n_tiles;
+            const int n0 = (tile % p.num_n_tiles) * p.BN;
+            const int i = quad * 32 + lane;              // row of the tile == TMEM lane
+            int s, y, x;
+            bool valid;
+            if (p.s2) {
+                const int tx = m_tile % p.tiles_x, ty = (m_tile / p.tiles_x) % p.tiles_y, bi = m_tile / (p.tiles_x * p.tiles_y);
+                const int bw = i % p.BW, bh = (i / p.BW) % p.BH, bn = i / (p.BW * p.BH);
+                s = bi * p.BI + bn;
+                y = ty * p.BH + bh;
+                x = tx * p.BW + bw;
+                valid = (s < p.gout.S) && (y < Ho) && (x < Wo);
+            } else {
+                const long long row = (long long)m_tile * kTileM + i;
+                const int plane = (Ho + 2) * (Wo + 2);
+                s = (int)(row / plane);
+                const int rem = (int)(row - (long long)s * plane);
+                const int py = rem / (Wo + 2), px = rem - py * (Wo + 2);
+                y = py - 1;
+                x = px - 1;
+                valid = (s < p.gout.S) && (py >= 1) && (py <= Ho) && (px >= 1) && (px <= Wo);
+            }
+            const long long opix_padded = ((long long)s * (Ho + 2) + (y + 1)) * (Wo + 2) + (x + 1);
+            const uint32_t elem_pix = (uint32_t)(y * Wo + x) * (uint32_t)ep.cout;      // dropout element index base
+            const int t_smp = ep.drop.enabled ? (s % ep.drop.T) : 0;
+            const int image = ep.drop.enabled ? (ep.drop.image0 + s / ep.drop.T) : 0;
+
+            mbar_wait(smem_u32(&ctl->acc_full[as]), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quad * 32) << 16);
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                uint32_t raw[16];
+                tmem_ld16(taddr + c0, raw);
+                tmem_ld_wait();
+                const int c = n0 + c0;
+                if (valid && c < ep.cout) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+                    if (ep.drop.enabled) {
+                        dropout8(v, ep.drop, (elem_pix + (uint32_t)c) >> 3, t_smp, image);
+                        dropout8(v + 8, ep.drop, ((elem_pix + (uint32_t)c) >> 3) + 1, t_smp, image);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] += __ldg(ep.bias + c + j);
+                        if (ep.leaky) v[j] = fmaxf(v[j], 0.1f * v[j]);
+                    }
+                    if (ep.out_mode == OUT_DENSE_F32) {
+                        float* o = reinterpret_cast<float*>(ep.out) + ((long long)(s * Ho + y) * Wo + x) * ep.ldc + c;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c + j < ep.cout) o[j] = v[j];
+                    } else {
+                        if (ep.residual) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(ep.residual) +
+                                                                             opix_padded * ep.ldc + c);
+                            uint4 r4[2] = {__ldg(rp), __ldg(rp + 1)};
+                            const __half2* rh = reinterpret_cast<const __half2*>(r4);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 f = __half22float2(rh[j]);
+                                v[2 * j] += f.x;
+                                v[2 * j + 1] += f.y;
+                            }
+                        }
+                        uint4 o4[2];
+                        __half2* oh = reinterpret_cast<__half2*>(o4);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                        __half* ob = reinterpret_cast<__half*>(ep.out);
+                        if (ep.out_mode == OUT_PADDED) {
+                            uint4* o = reinterpret_cast<uint4*>(ob + opix_padded * ep.ldc + c);
+                            o[0] = o4[0];
+                            o[1] = o4[1];
+                        } else {   // OUT_UPSAMPLE2: nearest-neighbour x2 -> four destination pixels
+#pragma unroll
+                            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                                for (int dx = 0; dx < 2; ++dx) {
+                                    const long long q = ((long long)s * (2 * Ho + 2) + (2 * y + dy + 1)) * (2 * Wo + 2) + (2 * x + dx + 1);
+                                    uint4* o = reinterpret_cast<uint4*>(ob + q * ep.ldc + c);
+                                    o[0] = o4[0];
+                                    o[1] = o4[1];
+                                }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty[as]));
+        }
+    }
+
+    // ---------------- teardown ----------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// --------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* estr, int swizzle_bytes) {
+    EncodeTiledFn fn = encode_fn();
+    BY_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = estr[i]; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return -3;
+    }
+    return 0;
+}
+
+// best (BW, BH, BI) with BW*BH*BI == 128 for a stride-2 output of S x Ho x Wo
+static void pick_patch(int S, int Ho, int Wo, int* BW, int* BH, int* BI) {
+    double best = -1;
+    for (int bw = 1; bw <= 128; bw *= 2)
+        for (int bh = 1; bw * bh <= 128; bh *= 2) {
+            const int bi = 128 / (bw * bh);
+            auto cdiv = [](int a, int b) { return (a + b - 1) / b; };
+            const double eff = (double)S * Ho * Wo / ((double)cdiv(S, bi) * bi * cdiv(Ho, bh) * bh * cdiv(Wo, bw) * bw);
+            // prefer wider rows on ties (longer contiguous TMA segments)
+            if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > *BW)) { best = eff; *BW = bw; *BH = bh; *BI = bi; }
+        }
+}
+
+int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
+    std::memset(L, 0, sizeof(*L));
+    UmmaParams& p = L->p;
+    const Geom& g = q.gin;
+    const int C1 = g.C, C2 = q.in2 ? q.c2 : 0;
+    BY_REQUIRE(q.k == 1 || q.k == 3, "kernel size must be 1 or 3 (layers.py:528)");
+    BY_REQUIRE(q.stride == 1 || (q.stride == 2 && q.k == 3 && !q.in2), "stride 2 only as the 3x3 downsample conv");
+    BY_REQUIRE(!(q.in2 && q.k != 1), "channel-concat input only for 1x1 convs");
+    BY_REQUIRE(C1 % 32 == 0 && C2 % 32 == 0, "channel counts must be multiples of 32");
+    BY_REQUIRE(q.cout_pad % 16 == 0, "padded cout must be a multiple of 16");
+    p.BK = (C1 % 64 == 0 && C2 % 64 == 0) ? 64 : 32;
+    p.taps = q.k * q.k;
+    p.kb1 = C1 / p.BK;
+    p.kb2 = C2 / p.BK;
+    p.BN = std::min(q.cout_pad, 256);
+    BY_REQUIRE(q.cout_pad % p.BN == 0, "cout_pad must be a multiple of the N tile");
+    p.num_n_tiles = q.cout_pad / p.BN;
+    p.in_PW = g.PW();
+    p.s2 = q.stride == 2;
+    p.gout.S = g.S;
+    p.gout.H = g.H / q.stride;
+    p.gout.W = g.W / q.stride;
+    p.gout.C = q.ep.cout;
+    if (q.ep.out_mode != OUT_DENSE_F32) BY_REQUIRE(q.ep.cout % 16 == 0 && q.ep.ldc % 8 == 0, "fp16 outputs need cout % 16 == 0");
+    p.ep = q.ep;
+    const int swz = p.BK * 2;                                     // 128B or 64B rows
+    p.sbo_bytes = 8 * swz;
+    p.layout_type = (swz == 128) ? 2u : 4u;                       // SWIZZLE_128B / SWIZZLE_64B
+    p.a_bytes = kTileM * swz;
+    p.b_bytes = p.BN * swz;
+    // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+    p.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const int budget = 227 * 1024 - 1024 - (int)sizeof(SmemCtl) - 64;
+    p.num_stages = std::max(2, std::min(kMaxStages, budget / (p.a_bytes + p.b_bytes)));
+    L->smem_bytes = p.num_stages * (p.a_bytes + p.b_bytes) + 1024 + sizeof(SmemCtl) + 64;
+
+    const uint32_t one[5] = {1, 1, 1, 1, 1};
+    if (!p.s2) {
+        const long long rows = g.rows();
+        p.num_m_tiles = (int)((rows + kTileM - 1) / kTileM);
+        uint64_t d1[2] = {(uint64_t)C1, (uint64_t)rows}, s1[1] = {(uint64_t)C1 * 2};
+        uint32_t box[2] = {(uint32_t)p.BK, (uint32_t)kTileM};
+        if (int e = make_map(&L->a1, q.in1, 2, d1, s1, box, one, swz)) return e;
+        if (q.in2) {
+            uint64_t d2[2] = {(uint64_t)C2, (uint64_t)rows}, s2[1] = {(uint64_t)C2 * 2};
+            if (int e = make_map(&L->a2, q.in2, 2, d2, s2, box, one, swz)) return e;
+        } else {
+            L->a2 = L->a1;
+        }
+    } else {
+        pick_patch(p.gout.S, p.gout.H, p.gout.W, &p.BW, &p.BH, &p.BI);
+        p.tiles_x = (p.gout.W + p.BW - 1) / p.BW;
+        p.tiles_y = (p.gout.H + p.BH - 1) / p.BH;
+        p.num_m_tiles = p.tiles_x * p.tiles_y * ((p.gout.S + p.BI - 1) / p.BI);
+        uint64_t d[4] = {(uint64_t)C1, (uint64_t)g.PW(), (uint64_t)g.PH(), (uint64_t)g.S};
+        uint64_t s[3] = {(uint64_t)C1 * 2, (uint64_t)C1 * 2 * g.PW(), (uint64_t)C1 * 2 * g.PW() * g.PH()};
+        uint32_t box[4] = {(uint32_t)p.BK, (uint32_t)(2 * p.BW), (uint32_t)(2 * p.BH), (uint32_t)p.BI};
+        uint32_t es[4] = {1, 2, 2, 1};
+        if (int e = make_map(&L->a1, q.in1, 4, d, s, box, es, swz)) return e;
+        L->a2 = L->a1;
+    }
+    {
+        const uint64_t K = (uint64_t)p.taps * (C1 + C2);
+        uint64_t d[2] = {K, (uint64_t)q.cout_pad}, s[1] = {K * 2};
+        uint32_t box[2] = {(uint32_t)p.BK, (uint32_t)p.BN};
+        if (int e = make_map(&L->b, q.w16, 2, d, s, box, one, swz)) return e;
+    }
+    p.num_tiles = p.num_m_tiles * p.num_n_tiles;
+    int dev = 0, sms = 0;
+    BY_CUDA(cudaGetDevice(&dev));
+    BY_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    L->grid = std::min(p.num_tiles, sms);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    BY_CUDA(attr_err);
+    return 0;
+}
+
+int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
+    conv_umma_kernel<<<L.grid, kThreads, L.smem_bytes, st>>>(L.a1, L.a2, L.b, L.p);
+    BY_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_conv_umma(const ConvProblem& q, cudaStream_t st) {
+    UmmaLaunch L;
+    if (int e = umma_prepare(q, &L)) return e;
+    return umma_launch(L, st);
+}
+
+}  // namespace byolo

@@ -1,0 +1,32 @@
+// Launch record of the tcgen05 conv kernel (conv_umma.cu): built once per layer of a plan, launched every forward.
+#pragma once
+#include "common.cuh"
+
+namespace byolo {
+
+struct UmmaParams {
+    int num_m_tiles, num_n_tiles, num_tiles;
+    int BN, BK, num_stages;
+    int a_bytes, b_bytes;          // bytes of one A / B stage tile
+    int taps;                      // 1 | 9
+    int kb1, kb2;                  // K blocks per tap read from in1 / in2
+    int in_PW;                     // padded width of the input (row shift of one filter row)
+    int s2;                        // stride-2 patch mode
+    int BW, BH, BI, tiles_x, tiles_y;
+    Geom gout;                     // un-padded output geometry
+    Epilogue ep;
+    uint32_t idesc;                // tcgen05 instruction descriptor
+    uint32_t sbo_bytes, layout_type;
+};
+
+struct UmmaLaunch {
+    CUtensorMap a1, a2, b;
+    UmmaParams p;
+    int grid;
+    int smem_bytes;
+};
+
+int umma_prepare(const ConvProblem& q, UmmaLaunch* out);
+int umma_launch(const UmmaLaunch& L, cudaStream_t st);
+
+}  // namespace byolo

@@ -1,0 +1,610 @@
+// libbyolo engine: weight folding/upload, per-batch execution plans (buffers, tensor maps, launch list) and the C ABI
+// declared in include/byolo.h.  The plan is this repo's replacement for the graph that
+// /root/reference/lib_yolo/yolov3.py:232-310 / 370-451 / 518-628 builds through model.ModelBuilder (model.py:20-185).
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "../../include/byolo.h"
+#include "common.cuh"
+#include "conv_umma.cuh"
+
+namespace byolo {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+struct LayerDef { int k, s, cin, cout, bn, dropout; };
+
+// layer table in creation order of the reference graph (darknet.py:7-39, yolov3.py:543-622)
+static std::vector<LayerDef> layer_table(int variant, int cls_cnt) {
+    std::vector<LayerDef> t;
+    t.push_back({3, 1, 3, 32, 1, 0});
+    int c = 32;
+    const int stage[5][2] = {{32, 1}, {64, 2}, {128, 8}, {256, 8}, {512, 4}};
+    for (auto& st : stage) {
+        t.push_back({3, 2, c, 2 * st[0], 1, 0});
+        c = 2 * st[0];
+        for (int b = 0; b < st[1]; ++b) {
+            t.push_back({1, 1, c, st[0], 1, 0});
+            t.push_back({3, 1, st[0], c, 1, 0});
+        }
+    }
+    const int det_ch = variant == BYOLO_STANDARD ? 3 * (5 + cls_cnt) : 3 * 2 * (5 + cls_cnt);
+    const int mc = variant == BYOLO_EPISTEMIC;
+    const int head[3][2] = {{512, 1024}, {256, 768}, {128, 384}};
+    for (int j = 0; j < 3; ++j) {
+        const int f = head[j][0];
+        if (j) t.push_back({1, 1, 2 * f, f, 1, 0});
+        t.push_back({1, 1, head[j][1], f, 1, mc});
+        t.push_back({3, 1, f, 2 * f, 1, mc});
+        t.push_back({1, 1, 2 * f, f, 1, mc});
+        t.push_back({3, 1, f, 2 * f, 1, mc});
+        t.push_back({1, 1, 2 * f, f, 1, mc});
+        t.push_back({3, 1, f, 2 * f, 1, 0});
+        t.push_back({1, 1, 2 * f, det_ch, 0, 0});
+    }
+    return t;
+}
+
+struct LayerWeights {
+    int K = 0, cout_pad = 0;
+    float* bias = nullptr;     // [cout_pad] BN shift or detection bias
+    __half* w16 = nullptr;     // [cout_pad, K]
+    float* w32 = nullptr;      // [K, cout_pad]
+    void release() {
+        cudaFree(bias); cudaFree(w16); cudaFree(w32);
+        bias = nullptr; w16 = nullptr; w32 = nullptr;
+    }
+};
+
+// Folds BN into (weights, shift) and uploads both layouts.  kernel: HWIO fp32; bn = beta,gamma,mean,var | nullptr.
+static int fold_and_upload(const LayerDef& d, const float* kernel, const float* bn, const float* bias, LayerWeights* out) {
+    const int K = d.k * d.k * d.cin;
+    const int cp = (d.cout + 15) / 16 * 16;
+    std::vector<float> scale(d.cout, 1.f), shift(cp, 0.f);
+    for (int c = 0; c < d.cout; ++c) {
+        if (bn) {
+            const float beta = bn[c], gamma = bn[d.cout + c], mean = bn[2 * d.cout + c], var = bn[3 * d.cout + c];
+            scale[c] = gamma / std::sqrt(var + 1e-5f);              // layers.py:511,516: epsilon=1e-05
+            shift[c] = beta - mean * scale[c];
+        } else {
+            shift[c] = bias ? bias[c] : 0.f;
+        }
+    }
+    std::vector<float> w32((size_t)K * cp, 0.f);
+    std::vector<__half> w16((size_t)cp * K, __float2half(0.f));
+    for (int kk = 0; kk < K; ++kk)
+        for (int c = 0; c < d.cout; ++c) {
+            const float v = kernel[(size_t)kk * d.cout + c] * scale[c];   // HWIO flattened == [K][cout]
+            w32[(size_t)kk * cp + c] = v;
+            w16[(size_t)c * K + kk] = __float2half_rn(v);
+        }
+    out->K = K;
+    out->cout_pad = cp;
+    BY_CUDA(cudaMalloc(&out->bias, sizeof(float) * cp));
+    BY_CUDA(cudaMalloc(&out->w32, sizeof(float) * w32.size()));
+    BY_CUDA(cudaMalloc(&out->w16, sizeof(__half) * w16.size()));
+    BY_CUDA(cudaMemcpy(out->bias, shift.data(), sizeof(float) * cp, cudaMemcpyHostToDevice));
+    BY_CUDA(cudaMemcpy(out->w32, w32.data(), sizeof(float) * w32.size(), cudaMemcpyHostToDevice));
+    BY_CUDA(cudaMemcpy(out->w16, w16.data(), sizeof(__half) * w16.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+struct Buffer {
+    void* ptr = nullptr;
+    Geom g{0, 0, 0, 0};
+    bool dense_f32 = false;
+    size_t bytes = 0;
+};
+
+enum StepKind { STEP_STEM, STEP_CONV, STEP_STACK };
+
+struct Step {
+    StepKind kind;
+    int layer = -1;
+    ConvProblem prob{};
+    UmmaLaunch ul{};
+    int out_buf = -1;
+    // stack
+    const void* src = nullptr;
+    void* dst = nullptr;
+    long long plane_bytes = 0;
+};
+
+struct Plan {
+    int B = 0;
+    std::vector<Buffer> bufs;
+    std::vector<Step> steps;
+    std::vector<int> conv_out;      // conv index -> buffer id
+    int raw_buf[3] = {-1, -1, -1};
+    float* rows_scratch = nullptr;  // [B,N,D] when the caller passes no rows buffer
+    float* img_stage = nullptr;     // device staging for byolo_detect_host
+    float* out_stage = nullptr;
+    int* cnt_stage = nullptr;
+    int stage_max_out = 0;
+    ~Plan() {
+        for (auto& b : bufs) cudaFree(b.ptr);
+        cudaFree(rows_scratch); cudaFree(img_stage); cudaFree(out_stage); cudaFree(cnt_stage);
+    }
+};
+
+}  // namespace byolo
+
+using namespace byolo;
+
+struct byolo_engine {
+    byolo_config cfg{};
+    std::vector<LayerDef> layers;
+    std::vector<LayerWeights> weights;
+    bool loaded = false;
+    std::map<int, std::unique_ptr<Plan>> plans;
+    Plan* last_plan = nullptr;     // plan of the most recent forward (byolo_get_activation)
+    int N = 0, D = 0, obj_idx = 0, cls_start = 0;
+    int gh[3], gw[3];
+    bool act_half() const { return cfg.precision != BYOLO_PREC_FP32; }
+    size_t esize() const { return act_half() ? 2 : 4; }
+    bool mc() const { return cfg.variant == BYOLO_EPISTEMIC; }
+    int samples(int B) const { return mc() ? B * cfg.T : B; }
+    ~byolo_engine() {
+        plans.clear();
+        for (auto& w : weights) w.release();
+    }
+};
+
+namespace byolo {
+
+static int new_buffer(byolo_engine* e, Plan* pl, int S, int H, int W, int C, bool dense_f32, int* id) {
+    Buffer b;
+    b.g = Geom{S, H, W, C};
+    b.dense_f32 = dense_f32;
+    b.bytes = dense_f32 ? (size_t)S * H * W * C * 4 : (size_t)b.g.rows() * C * e->esize();
+    BY_CUDA(cudaMalloc(&b.ptr, b.bytes));
+    BY_CUDA(cudaMemset(b.ptr, 0, b.bytes));      // padded buffers: the border is written exactly once, here
+    pl->bufs.push_back(b);
+    *id = (int)pl->bufs.size() - 1;
+    return 0;
+}
+
+// Appends the conv step of layer `li`.  in2 < 0: single input.  residual < 0: none.
+static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int residual, int out_mode, int drop_id, int* out_id) {
+    const LayerDef& d = e->layers[li];
+    const LayerWeights& w = e->weights[li];
+    const Buffer bin = pl->bufs[in1];
+    BY_REQUIRE(bin.g.C + (in2 >= 0 ? pl->bufs[in2].g.C : 0) == d.cin, "plan wiring: channel mismatch");
+    const int Ho = bin.g.H / d.s, Wo = bin.g.W / d.s;
+    int ob;
+    if (out_mode == OUT_DENSE_F32) {
+        if (int r = new_buffer(e, pl, bin.g.S, Ho, Wo, d.cout, true, &ob)) return r;
+    } else if (out_mode == OUT_UPSAMPLE2) {
+        if (int r = new_buffer(e, pl, bin.g.S, 2 * Ho, 2 * Wo, d.cout, false, &ob)) return r;
+    } else {
+        if (int r = new_buffer(e, pl, bin.g.S, Ho, Wo, d.cout, false, &ob)) return r;
+    }
+    Step st;
+    st.kind = STEP_CONV;
+    st.layer = li;
+    st.out_buf = ob;
+    ConvProblem& p = st.prob;
+    p.in1 = bin.ptr;
+    p.in2 = in2 >= 0 ? pl->bufs[in2].ptr : nullptr;
+    p.gin = bin.g;
+    p.c2 = in2 >= 0 ? pl->bufs[in2].g.C : 0;
+    p.k = d.k;
+    p.stride = d.s;
+    p.cout_pad = w.cout_pad;
+    p.w16 = w.w16;
+    p.w32 = w.w32;
+    p.ep.bias = w.bias;
+    p.ep.residual = residual >= 0 ? pl->bufs[residual].ptr : nullptr;
+    p.ep.out = pl->bufs[ob].ptr;
+    p.ep.out_mode = out_mode;
+    p.ep.ldc = d.cout;
+    p.ep.cout = d.cout;
+    p.ep.leaky = d.bn;
+    p.ep.drop.enabled = drop_id >= 0;
+    p.ep.drop.layer_id = drop_id;
+    p.ep.drop.T = e->cfg.T;
+    p.ep.drop.thr16 = (uint32_t)std::lround((double)e->cfg.drop_prob * 65536.0);
+    p.ep.drop.keep_scale = 1.0f / (1.0f - e->cfg.drop_prob);
+    if (e->cfg.precision == BYOLO_PREC_FP16)
+        if (int r = umma_prepare(p, &st.ul)) return r;
+    pl->steps.push_back(st);
+    pl->conv_out[li] = ob;
+    *out_id = ob;
+    return 0;
+}
+
+static int add_stack(byolo_engine* e, Plan* pl, int src, int B, int T, int* out_id) {
+    if (T == 1) { *out_id = src; return 0; }
+    const Buffer bs = pl->bufs[src];
+    int ob;
+    if (int r = new_buffer(e, pl, B * T, bs.g.H, bs.g.W, bs.g.C, false, &ob)) return r;
+    Step st;
+    st.kind = STEP_STACK;
+    st.src = bs.ptr;
+    st.dst = pl->bufs[ob].ptr;
+    st.plane_bytes = (long long)bs.g.PH() * bs.g.PW() * bs.g.C * e->esize();
+    pl->steps.push_back(st);
+    *out_id = ob;
+    return 0;
+}
+
+static int build_plan(byolo_engine* e, int B, Plan* pl) {
+    const byolo_config& c = e->cfg;
+    pl->B = B;
+    pl->conv_out.assign(e->layers.size(), -1);
+    const int T = e->mc() ? c.T : 1;
+    int li = 0, cur, tmp;
+    // ---- darknet53 (darknet.py:7-39) ----
+    if (int r = new_buffer(e, pl, B, c.height, c.width, 32, false, &cur)) return r;
+    {
+        Step st;
+        st.kind = STEP_STEM;
+        st.layer = 0;
+        st.out_buf = cur;
+        pl->steps.push_back(st);
+        pl->conv_out[0] = cur;
+        li = 1;
+    }
+    const int blocks[5] = {1, 2, 8, 8, 4};
+    int taps[5];
+    for (int sidx = 0; sidx < 5; ++sidx) {
+        if (int r = add_conv(e, pl, li++, cur, -1, -1, OUT_PADDED, -1, &cur)) return r;            // downsample
+        for (int b = 0; b < blocks[sidx]; ++b) {                                                   // residual block
+            if (int r = add_conv(e, pl, li++, cur, -1, -1, OUT_PADDED, -1, &tmp)) return r;
+            if (int r = add_conv(e, pl, li++, tmp, -1, cur, OUT_PADDED, -1, &cur)) return r;       // + shortcut (model.py:96-99)
+        }
+        taps[sidx] = cur;
+    }
+    const int l36 = taps[2], l61 = taps[3], l74 = taps[4];
+    // ---- det_net_1..3 (yolov3.py:543-622) ----
+    int drop_next = 0;
+    auto drop_id = [&](int layer) {
+        return (e->layers[layer].dropout && e->mc() && !c.standard_test_dropout) ? drop_next++ : -1;
+    };
+    int route_src = -1;
+    const int srcs[3] = {l74, l61, l36};
+    for (int j = 0; j < 3; ++j) {
+        int x1, x2 = -1;
+        if (j == 0) {
+            if (int r = add_stack(e, pl, srcs[0], B, T, &x1)) return r;                            // stack_feature_map(-1, T)
+        } else {
+            if (int r = add_conv(e, pl, li++, route_src, -1, -1, OUT_UPSAMPLE2, -1, &x1)) return r;  // conv 84/96 + upsample
+            if (int r = add_stack(e, pl, srcs[j], B, T, &x2)) return r;                            // stack_feature_map(61|36, T)
+        }
+        int x = x1, c5 = -1;
+        for (int i = 0; i < 6; ++i) {
+            const int l = li++;
+            if (int r = add_conv(e, pl, l, x, (i == 0) ? x2 : -1, -1, OUT_PADDED, drop_id(l), &x)) return r;
+            if (i == 4) c5 = x;
+        }
+        if (int r = add_conv(e, pl, li++, x, -1, -1, OUT_DENSE_F32, -1, &pl->raw_buf[j])) return r;   // detection conv
+        route_src = c5;                                                                            // route([-3])
+    }
+    BY_REQUIRE(li == (int)e->layers.size(), "plan did not consume all layers");
+    BY_CUDA(cudaMalloc(&pl->rows_scratch, sizeof(float) * (size_t)B * e->N * e->D));
+    return 0;
+}
+
+static int get_plan(byolo_engine* e, int B, Plan** out) {
+    BY_REQUIRE(e->loaded, "byolo_load_weights has not been called");
+    BY_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch size out of range");
+    auto it = e->plans.find(B);
+    if (it == e->plans.end()) {
+        std::unique_ptr<Plan> pl(new Plan());
+        if (int r = build_plan(e, B, pl.get())) return r;
+        it = e->plans.emplace(B, std::move(pl)).first;
+    }
+    *out = it->second.get();
+    e->last_plan = *out;
+    return 0;
+}
+
+static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t seed, int image0, float* rows, cudaStream_t st) {
+    const byolo_config& c = e->cfg;
+    for (Step& s : pl->steps) {
+        if (s.kind == STEP_STEM) {
+            const LayerWeights& w = e->weights[0];
+            if (int r = launch_stem(img, pl->B, c.height, c.width, w.w32, w.bias, pl->bufs[s.out_buf].ptr, e->act_half(), st)) return r;
+        } else if (s.kind == STEP_STACK) {
+            if (int r = launch_stack(s.src, s.dst, s.plane_bytes, pl->B, c.T, st)) return r;
+        } else {
+            if (c.precision == BYOLO_PREC_FP16) {
+                Dropout& d = s.ul.p.ep.drop;
+                d.seed_lo = (uint32_t)seed; d.seed_hi = (uint32_t)(seed >> 32); d.image0 = image0;
+                if (int r = umma_launch(s.ul, st)) return r;
+            } else {
+                Dropout& d = s.prob.ep.drop;
+                d.seed_lo = (uint32_t)seed; d.seed_hi = (uint32_t)(seed >> 32); d.image0 = image0;
+                if (int r = launch_conv_simt(s.prob, e->act_half(), st)) return r;
+            }
+        }
+    }
+    DecodeProblem dp{};
+    dp.variant = c.variant;
+    dp.B = pl->B;
+    dp.T = e->mc() ? c.T : 1;
+    dp.cls_cnt = c.cls_cnt;
+    for (int j = 0; j < 3; ++j) {
+        dp.gh[j] = e->gh[j]; dp.gw[j] = e->gw[j];
+        dp.raw[j] = (const float*)pl->bufs[pl->raw_buf[j]].ptr;
+        dp.ld[j] = pl->bufs[pl->raw_buf[j]].g.C;
+    }
+    for (int i = 0; i < 9; ++i) { dp.prior_h[i] = c.prior_h[i]; dp.prior_w[i] = c.prior_w[i]; }
+    dp.rows = rows;
+    dp.N = e->N;
+    dp.D = e->D;
+    return launch_decode(dp, st);
+}
+
+}  // namespace byolo
+
+// =====================================================================================================================
+//                                                       C ABI
+// =====================================================================================================================
+extern "C" {
+
+int byolo_version(void) { return 1; }
+const char* byolo_last_error(void) { return g_err.c_str(); }
+
+int byolo_create(const byolo_config* cfg, byolo_handle* out) {
+    BY_REQUIRE(cfg && out, "null argument");
+    BY_REQUIRE(cfg->variant >= 0 && cfg->variant <= 2, "unknown variant");
+    BY_REQUIRE(cfg->height > 0 && cfg->width > 0 && cfg->height % 32 == 0 && cfg->width % 32 == 0,
+               "image size must be a multiple of 32 (yolov3.py:207-211)");
+    BY_REQUIRE(cfg->cls_cnt >= 1 && cfg->cls_cnt <= 16, "cls_cnt must be in [1,16]");
+    BY_REQUIRE(cfg->max_batch >= 1, "max_batch must be >= 1");
+    BY_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, "unknown precision");
+    BY_REQUIRE(cfg->variant != BYOLO_EPISTEMIC || cfg->T >= 1, "epistemic model needs T >= 1 (yolov3.py:467-468)");
+    BY_REQUIRE(cfg->drop_prob >= 0.f && cfg->drop_prob < 1.f, "drop_prob must be in [0,1)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: libbyolo has no CPU fallback");
+        return -2;
+    }
+    byolo_engine* e = new byolo_engine();
+    e->cfg = *cfg;
+    if (cfg->variant != BYOLO_EPISTEMIC) e->cfg.T = 1;
+    e->layers = layer_table(cfg->variant, cfg->cls_cnt);
+    e->N = 0;
+    for (int j = 0; j < 3; ++j) {
+        e->gh[j] = cfg->height / (32 >> j);
+        e->gw[j] = cfg->width / (32 >> j);
+        e->N += 3 * e->gh[j] * e->gw[j];
+    }
+    const int C = cfg->cls_cnt;
+    if (cfg->variant == BYOLO_STANDARD) { e->D = 5 + C; e->obj_idx = 4; e->cls_start = 5; }
+    if (cfg->variant == BYOLO_ALEATORIC) { e->D = 14 + C; e->obj_idx = 9; e->cls_start = 11; }
+    if (cfg->variant == BYOLO_EPISTEMIC) { e->D = 21 + C; e->obj_idx = 14; e->cls_start = 17; }
+    *out = e;
+    return 0;
+}
+
+int byolo_destroy(byolo_handle h) {
+    if (h) { cudaDeviceSynchronize(); delete h; }
+    return 0;
+}
+
+int byolo_load_weights(byolo_handle h, const void* blob, size_t bytes) {
+    BY_REQUIRE(h && blob, "null argument");
+    const int32_t* hdr = (const int32_t*)blob;
+    BY_REQUIRE(bytes >= 8 && hdr[0] == 0x31575942, "not a BYW1 weight blob");
+    const int n = hdr[1];
+    BY_REQUIRE(n == (int)h->layers.size(), "weight blob has the wrong number of layers");
+    BY_REQUIRE(bytes >= 8 + (size_t)24 * n, "weight blob truncated");
+    const int32_t* tab = hdr + 2;
+    size_t off = 8 + (size_t)24 * n;
+    for (auto& w : h->weights) w.release();
+    h->weights.assign(n, LayerWeights());
+    h->plans.clear();
+    h->last_plan = nullptr;
+    for (int i = 0; i < n; ++i) {
+        const LayerDef& d = h->layers[i];
+        BY_REQUIRE(tab[6 * i] == d.k && tab[6 * i + 1] == d.s && tab[6 * i + 2] == d.cin && tab[6 * i + 3] == d.cout &&
+                       tab[6 * i + 4] == d.bn,
+                   "weight blob layer table does not match the model variant");
+        const size_t nv = (size_t)(d.bn ? 4 : 1) * d.cout, nk = (size_t)d.k * d.k * d.cin * d.cout;
+        BY_REQUIRE(off + 4 * (nv + nk) <= bytes, "weight blob truncated");
+        const float* vec = (const float*)((const char*)blob + off);
+        const float* kern = vec + nv;
+        if (int r = fold_and_upload(d, kern, d.bn ? vec : nullptr, d.bn ? nullptr : vec, &h->weights[i])) return r;
+        off += 4 * (nv + nk);
+    }
+    BY_REQUIRE(off == bytes, "weight blob has trailing bytes");     // darknet.py:66 `assert ptr == len(weights)`
+    BY_CUDA(cudaDeviceSynchronize());
+    h->loaded = true;
+    return 0;
+}
+
+int byolo_output_shape(byolo_handle h, int32_t* N, int32_t* D, int32_t* obj_idx, int32_t* cls_start_idx) {
+    BY_REQUIRE(h, "null handle");
+    if (N) *N = h->N;
+    if (D) *D = h->D;
+    if (obj_idx) *obj_idx = h->obj_idx;
+    if (cls_start_idx) *cls_start_idx = h->cls_start;
+    return 0;
+}
+
+int byolo_forward(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed, int32_t image_index0, float* rows_dev,
+                  void* stream) {
+    BY_REQUIRE(h && img_dev && rows_dev, "null argument");
+    Plan* pl;
+    if (int r = get_plan(h, B, &pl)) return r;
+    return run_forward(h, pl, img_dev, seed, image_index0, rows_dev, (cudaStream_t)stream);
+}
+
+int byolo_nms(const float* rows_dev, int32_t B, int32_t N, int32_t D, int32_t obj_idx, float iou_thr, int32_t max_out,
+              float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev, void* stream) {
+    BY_REQUIRE(rows_dev && out_rows_dev && out_count_dev, "null argument");
+    return launch_nms(rows_dev, B, N, D, obj_idx, iou_thr, max_out, out_rows_dev, out_idx_dev, out_count_dev, nullptr, 0,
+                      (cudaStream_t)stream);
+}
+
+int byolo_detect(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
+                 int32_t max_out, float* rows_dev, float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev,
+                 void* stream) {
+    BY_REQUIRE(h && img_dev && out_rows_dev && out_count_dev, "null argument");
+    Plan* pl;
+    if (int r = get_plan(h, B, &pl)) return r;
+    float* rows = rows_dev ? rows_dev : pl->rows_scratch;
+    if (int r = run_forward(h, pl, img_dev, seed, image_index0, rows, (cudaStream_t)stream)) return r;
+    return launch_nms(rows, B, h->N, h->D, h->obj_idx, iou_thr, max_out, out_rows_dev, out_idx_dev, out_count_dev, nullptr, 0,
+                      (cudaStream_t)stream);
+}
+
+int byolo_detect_host(byolo_handle h, const float* img_host, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
+                      int32_t max_out, float* out_rows_host, int32_t* out_count_host, void* stream) {
+    BY_REQUIRE(h && img_host && out_rows_host && out_count_host, "null argument");
+    Plan* pl;
+    if (int r = get_plan(h, B, &pl)) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t img_bytes = sizeof(float) * (size_t)B * h->cfg.height * h->cfg.width * 3;
+    if (!pl->img_stage) BY_CUDA(cudaMalloc(&pl->img_stage, img_bytes));
+    if (pl->stage_max_out < max_out) {
+        cudaFree(pl->out_stage); cudaFree(pl->cnt_stage);
+        pl->out_stage = nullptr; pl->cnt_stage = nullptr;
+        BY_CUDA(cudaMalloc(&pl->out_stage, sizeof(float) * (size_t)B * max_out * h->D));
+        BY_CUDA(cudaMalloc(&pl->cnt_stage, sizeof(int) * B));
+        pl->stage_max_out = max_out;
+    }
+    BY_CUDA(cudaMemcpyAsync(pl->img_stage, img_host, img_bytes, cudaMemcpyHostToDevice, st));
+    if (int r = byolo_detect(h, pl->img_stage, B, seed, image_index0, iou_thr, max_out, nullptr, pl->out_stage, nullptr,
+                             pl->cnt_stage, stream))
+        return r;
+    BY_CUDA(cudaMemcpyAsync(out_rows_host, pl->out_stage, sizeof(float) * (size_t)B * max_out * h->D, cudaMemcpyDeviceToHost, st));
+    BY_CUDA(cudaMemcpyAsync(out_count_host, pl->cnt_stage, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    BY_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int byolo_decode(byolo_handle h, const float* raw0_dev, const float* raw1_dev, const float* raw2_dev, int32_t B,
+                 float* rows_dev, void* stream) {
+    BY_REQUIRE(h && raw0_dev && raw1_dev && raw2_dev && rows_dev, "null argument");
+    const byolo_config& c = h->cfg;
+    DecodeProblem dp{};
+    dp.variant = c.variant;
+    dp.B = B;
+    dp.T = h->mc() ? c.T : 1;
+    dp.cls_cnt = c.cls_cnt;
+    const float* raws[3] = {raw0_dev, raw1_dev, raw2_dev};
+    const int det_ch = h->layers.back().cout;
+    for (int j = 0; j < 3; ++j) { dp.gh[j] = h->gh[j]; dp.gw[j] = h->gw[j]; dp.raw[j] = raws[j]; dp.ld[j] = det_ch; }
+    for (int i = 0; i < 9; ++i) { dp.prior_h[i] = c.prior_h[i]; dp.prior_w[i] = c.prior_w[i]; }
+    dp.rows = rows_dev;
+    dp.N = h->N;
+    dp.D = h->D;
+    return launch_decode(dp, (cudaStream_t)stream);
+}
+
+int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_dev, int32_t S, int32_t H, int32_t W,
+                     int32_t cin1, int32_t cin2, int32_t k, int32_t stride, int32_t cout, const float* kernel_host,
+                     const float* bn_host, const float* bias_host, const float* residual_dev, int32_t upsample,
+                     int32_t dropout_layer, int32_t T, uint64_t seed, int32_t image_index0, float drop_prob, float* out_dev,
+                     void* stream) {
+    BY_REQUIRE(in1_dev && kernel_host && out_dev, "null argument");
+    BY_REQUIRE(precision >= 0 && precision <= 2, "unknown precision");
+    BY_REQUIRE((bn_host != nullptr) != (bias_host != nullptr), "pass exactly one of bn / bias");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool half = precision != BYOLO_PREC_FP32;
+    const size_t es = half ? 2 : 4;
+    LayerDef d{k, stride, cin1 + cin2, cout, bn_host != nullptr, dropout_layer >= 0};
+    LayerWeights w;
+    int rc = fold_and_upload(d, kernel_host, bn_host, bias_host, &w);
+    void *p1 = nullptr, *p2 = nullptr, *pr = nullptr, *po = nullptr;
+    const Geom g1{S, H, W, cin1}, g2{S, H, W, cin2};
+    const int Ho = H / stride, Wo = W / stride;
+    const bool dense = bn_host == nullptr;
+    const Geom go{S, upsample ? 2 * Ho : Ho, upsample ? 2 * Wo : Wo, cout};
+    auto alloc0 = [&](void** p, size_t bytes) {
+        if (rc) return;
+        if (cudaMalloc(p, bytes) != cudaSuccess || cudaMemsetAsync(*p, 0, bytes, st) != cudaSuccess) {
+            set_error("byolo_conv_layer: allocation failed");
+            rc = -2;
+        }
+    };
+    alloc0(&p1, (size_t)g1.rows() * cin1 * es);
+    if (in2_dev) alloc0(&p2, (size_t)g2.rows() * cin2 * es);
+    if (residual_dev) alloc0(&pr, (size_t)go.rows() * cout * es);
+    alloc0(&po, dense ? (size_t)S * Ho * Wo * cout * 4 : (size_t)go.rows() * cout * es);
+    if (!rc) rc = launch_pack(in1_dev, p1, g1, half, st);
+    if (!rc && in2_dev) rc = launch_pack(in2_dev, p2, g2, half, st);
+    if (!rc && residual_dev) rc = launch_pack(residual_dev, pr, go, half, st);
+    if (!rc) {
+        ConvProblem p{};
+        p.in1 = p1; p.in2 = p2; p.gin = g1; p.c2 = cin2; p.k = k; p.stride = stride;
+        p.cout_pad = w.cout_pad; p.w16 = w.w16; p.w32 = w.w32;
+        p.ep.bias = w.bias; p.ep.residual = pr; p.ep.out = po;
+        p.ep.out_mode = dense ? OUT_DENSE_F32 : (upsample ? OUT_UPSAMPLE2 : OUT_PADDED);
+        p.ep.ldc = cout; p.ep.cout = cout; p.ep.leaky = d.bn;
+        p.ep.drop.enabled = dropout_layer >= 0;
+        p.ep.drop.layer_id = dropout_layer; p.ep.drop.T = T > 0 ? T : 1; p.ep.drop.image0 = image_index0;
+        p.ep.drop.seed_lo = (uint32_t)seed; p.ep.drop.seed_hi = (uint32_t)(seed >> 32);
+        p.ep.drop.thr16 = (uint32_t)std::lround((double)drop_prob * 65536.0);
+        p.ep.drop.keep_scale = 1.0f / (1.0f - drop_prob);
+        rc = (precision == BYOLO_PREC_FP16) ? launch_conv_umma(p, st) : launch_conv_simt(p, half, st);
+    }
+    if (!rc) {
+        if (dense) {
+            if (cudaMemcpyAsync(out_dev, po, (size_t)S * Ho * Wo * cout * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = -2;
+        } else {
+            rc = launch_unpack(po, out_dev, go, half, st);
+        }
+    }
+    const cudaError_t se = cudaStreamSynchronize(st);
+    if (!rc && se != cudaSuccess) {
+        set_error(std::string("byolo_conv_layer: ") + cudaGetErrorString(se));
+        rc = -2;
+    }
+    cudaFree(p1); cudaFree(p2); cudaFree(pr); cudaFree(po);
+    w.release();
+    return rc;
+}
+
+int byolo_get_activation(byolo_handle h, int32_t conv_index, float* dst_dev, size_t capacity, int32_t shape[4], void* stream) {
+    BY_REQUIRE(h && dst_dev && shape, "null argument");
+    BY_REQUIRE(h->last_plan != nullptr, "no forward pass has run yet");
+    Plan* pl = h->last_plan;
+    BY_REQUIRE(conv_index >= 0 && conv_index < (int)pl->conv_out.size(), "conv index out of range");
+    const Buffer& b = pl->bufs[pl->conv_out[conv_index]];
+    shape[0] = b.g.S; shape[1] = b.g.H; shape[2] = b.g.W; shape[3] = b.g.C;
+    const size_t n = (size_t)b.g.S * b.g.H * b.g.W * b.g.C;
+    BY_REQUIRE(capacity >= n, "destination too small");
+    if (b.dense_f32) {
+        BY_CUDA(cudaMemcpyAsync(dst_dev, b.ptr, n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return 0;
+    }
+    return launch_unpack(b.ptr, dst_dev, b.g, h->act_half(), (cudaStream_t)stream);
+}
+
+int byolo_launch_count(byolo_handle h, int32_t B) {
+    BY_REQUIRE(h, "null handle");
+    Plan* pl;
+    if (int r = get_plan(h, B, &pl)) return r;
+    return (int)pl->steps.size() + 2;      // + decode + nms
+}
+
+double byolo_flops_per_image(byolo_handle h) {
+    if (!h) return 0.0;
+    double backbone = 0, head = 0;
+    int Hc = h->cfg.height, Wc = h->cfg.width;
+    // spatial size per layer follows the plan: backbone strides, head grids
+    int li = 0;
+    auto fl = [&](const LayerDef& d, int Ho, int Wo) { return 2.0 * d.k * d.k * d.cin * d.cout * Ho * Wo; };
+    backbone += fl(h->layers[li++], Hc, Wc);
+    const int blocks[5] = {1, 2, 8, 8, 4};
+    for (int s = 0; s < 5; ++s) {
+        Hc /= 2; Wc /= 2;
+        backbone += fl(h->layers[li++], Hc, Wc);
+        for (int b = 0; b < 2 * blocks[s]; ++b) backbone += fl(h->layers[li++], Hc, Wc);
+    }
+    for (int j = 0; j < 3; ++j) {
+        if (j) head += fl(h->layers[li++], h->gh[j - 1], h->gw[j - 1]);
+        for (int i = 0; i < 7; ++i) head += fl(h->layers[li++], h->gh[j], h->gw[j]);
+    }
+    return backbone + head * (h->mc() ? h->cfg.T : 1);
+}
+
+}  // extern "C"

@@ -142,6 +142,7 @@ class Forward:
 
     def _run_one(self, x, T, seed, image):
         L = []                       # ModelBuilder.__layers
+        fused = {}                   # conv index -> its output as the engine stores it (incl. the fused residual add)
         ci = [0]                     # next conv weight index
         di = [0]                     # next dropout layer id
         bayes = T is not None
@@ -155,6 +156,7 @@ class Forward:
                 di[0] += 1
             out = self.conv(inp if idx == 0 else self._round(inp), idx, drop)   # emulate: operands are stored rounded
             L.append(out)
+            fused[idx] = out
             return out
 
         # darknet53: conv, then 5 x (downsample, n x residual block)      darknet.py:7-39
@@ -165,6 +167,7 @@ class Forward:
                 conv(L[-1])
                 conv(L[-1])
                 L.append(self._round(L[-1] + self._round(L[-3])))   # residual: after the activation, model.py:96-99
+                fused[ci[0] - 1] = L[-1]
         assert len(L) == 75
         l36, l61, l74 = L[36], L[61], L[74]
         if bayes:                                             # stack_feature_map, layers.py:595-597
@@ -189,4 +192,6 @@ class Forward:
         out = {'raw': raws}
         if self.keep_layers:
             out['layers'] = [t.permute(0, 2, 3, 1).contiguous().numpy() for t in L]
+            out['conv_out'] = {i: self._round(t).permute(0, 2, 3, 1).contiguous().numpy() if self.specs[i]['bn']
+                               else t.permute(0, 2, 3, 1).contiguous().numpy() for i, t in fused.items()}
         return out

@@ -125,7 +125,10 @@ struct Plan {
     float* out_stage = nullptr;
     int* cnt_stage = nullptr;
     int stage_max_out = 0;
+    std::vector<cudaEvent_t> ev;    // profiling: steps.size() + 3 events (one before each launch, decode, nms, end)
+    bool ev_recorded = false;
     ~Plan() {
+        for (auto& x : ev) cudaEventDestroy(x);
         for (auto& b : bufs) cudaFree(b.ptr);
         cudaFree(rows_scratch); cudaFree(img_stage); cudaFree(out_stage); cudaFree(cnt_stage);
     }
@@ -142,6 +145,7 @@ struct byolo_engine {
     bool loaded = false;
     std::map<int, std::unique_ptr<Plan>> plans;
     Plan* last_plan = nullptr;     // plan of the most recent forward (byolo_get_activation)
+    bool profiling = false;
     int N = 0, D = 0, obj_idx = 0, cls_start = 0;
     int gh[3], gw[3];
     bool act_half() const { return cfg.precision != BYOLO_PREC_FP32; }
@@ -305,7 +309,14 @@ static int get_plan(byolo_engine* e, int B, Plan** out) {
 
 static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t seed, int image0, float* rows, cudaStream_t st) {
     const byolo_config& c = e->cfg;
+    const bool prof = e->profiling;
+    if (prof && pl->ev.empty()) {
+        pl->ev.resize(pl->steps.size() + 3);
+        for (auto& x : pl->ev) BY_CUDA(cudaEventCreate(&x));
+    }
+    size_t ei = 0;
     for (Step& s : pl->steps) {
+        if (prof) BY_CUDA(cudaEventRecord(pl->ev[ei++], st));
         if (s.kind == STEP_STEM) {
             const LayerWeights& w = e->weights[0];
             if (int r = launch_stem(img, pl->B, c.height, c.width, w.w32, w.bias, pl->bufs[s.out_buf].ptr, e->act_half(), st)) return r;
@@ -337,7 +348,10 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
     dp.rows = rows;
     dp.N = e->N;
     dp.D = e->D;
-    return launch_decode(dp, st);
+    if (prof) BY_CUDA(cudaEventRecord(pl->ev[ei++], st));
+    if (int r = launch_decode(dp, st)) return r;
+    if (prof) { BY_CUDA(cudaEventRecord(pl->ev[ei++], st)); pl->ev_recorded = false; }
+    return 0;
 }
 
 }  // namespace byolo
@@ -451,8 +465,45 @@ int byolo_detect(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed,
     if (int r = get_plan(h, B, &pl)) return r;
     float* rows = rows_dev ? rows_dev : pl->rows_scratch;
     if (int r = run_forward(h, pl, img_dev, seed, image_index0, rows, (cudaStream_t)stream)) return r;
-    return launch_nms(rows, B, h->N, h->D, h->obj_idx, iou_thr, max_out, out_rows_dev, out_idx_dev, out_count_dev, nullptr, 0,
-                      (cudaStream_t)stream);
+    if (int r = launch_nms(rows, B, h->N, h->D, h->obj_idx, iou_thr, max_out, out_rows_dev, out_idx_dev, out_count_dev, nullptr, 0,
+                           (cudaStream_t)stream))
+        return r;
+    if (h->profiling) { BY_CUDA(cudaEventRecord(pl->ev.back(), (cudaStream_t)stream)); pl->ev_recorded = true; }
+    return 0;
+}
+
+int byolo_profile(byolo_handle h, int32_t enable) {
+    BY_REQUIRE(h, "null handle");
+    h->profiling = enable != 0;
+    return 0;
+}
+
+int byolo_profile_read(byolo_handle h, float* ms, int32_t* kind, int32_t* layer, double* flops, int32_t capacity) {
+    BY_REQUIRE(h && ms && kind && layer && flops, "null argument");
+    Plan* pl = h->last_plan;
+    BY_REQUIRE(pl && pl->ev_recorded, "no profiled byolo_detect has completed");
+    const int n = (int)pl->steps.size() + 2;
+    BY_REQUIRE(capacity >= n, "capacity too small");
+    BY_CUDA(cudaEventSynchronize(pl->ev.back()));
+    for (int i = 0; i < n; ++i) {
+        BY_CUDA(cudaEventElapsedTime(&ms[i], pl->ev[i], pl->ev[i + 1]));
+        flops[i] = 0.0;
+        if (i < (int)pl->steps.size()) {
+            const Step& s = pl->steps[i];
+            kind[i] = (int)s.kind;
+            layer[i] = s.layer;
+            if (s.kind != STEP_STACK) {
+                const LayerDef& d = h->layers[s.layer];
+                const Buffer& ob = pl->bufs[s.out_buf];
+                const int up = (s.kind == STEP_CONV && s.prob.ep.out_mode == OUT_UPSAMPLE2) ? 4 : 1;
+                flops[i] = 2.0 * d.k * d.k * d.cin * d.cout * (double)ob.g.S * ob.g.H * ob.g.W / up;
+            }
+        } else {
+            kind[i] = 3 + (i - (int)pl->steps.size());      // 3 decode, 4 nms
+            layer[i] = -1;
+        }
+    }
+    return n;
 }
 
 int byolo_detect_host(byolo_handle h, const float* img_host, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,

@@ -1,0 +1,233 @@
+#!/usr/bin/env python
+"""Benchmark of the detection hot path (BASELINE.json metric: images/sec at 608x608, T=10 MC samples).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = one pass of the hot path (backbone once + head x T + decode + NMS(1000)) over one batch of B=16 synthetic
+608x608 images per GPU (BASELINE.json configs[2]); weights are random-init (byolo.weights.synthetic, seed 0).
+Prints ONE JSON line (contract in the task statement): `value` = device-resident throughput, `e2e` = the same metric
+through byolo_detect_host (pinned host images in, host detections out, copies inside the timed region),
+`roofline` for the dominant kernel (tcgen05 conv stack, tensor bound), `cpu_baseline` = the oracle port on host cores.
+`--impl reference` times the reference arm: the CPU restatement of the reference path (TensorFlow 1.x is not
+installable here) on all host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'bayesian-yolov3_b200')]
+
+METRIC = 'images/sec at 608x608, T=10 MC samples (epistemic, incl. decode + NMS)'
+WORKLOAD = dict(workload='configs[2]: epistemic MC-dropout T=10, batch 16/GPU, 608x608, cls_cnt 2, NMS cap 1000',
+                variant='epistemic', img=608, T=10, batch_per_gpu=16, cls_cnt=2, max_out=1000)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['bf16_tflops_sustained']), float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json, sustained bf16)'
+    except Exception:
+        return 1400.0, 6650.0, 'fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(',')])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows)]
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def cpu_oracle_rate(n_images, T, img, threads=None):
+    """Oracle port of the reference path on host cores: forward (torch CPU fp32) + decode + NMS.  Returns img/s."""
+    import torch
+    from byolo import priors as P, weights as W
+    from oracle import decode as D, net as ON, nms as ONMS
+    if threads:
+        torch.set_num_threads(threads)
+    pri = P.as_scale_list(P.by_stride('ECP_9_PRIORS'))
+    w = W.synthetic('epistemic', 2, 0)
+    fwd = ON.Forward('epistemic', w, 2, torch.float32)
+    imgs = np.random.default_rng(103).random((n_images, img, img, 3), dtype=np.float32)
+    t0 = time.perf_counter()
+    for b in range(n_images):
+        res = fwd.run(imgs[b:b + 1], T=T, seed=1003, image_index0=b)
+        rows = D.rows_from_raw('epistemic', res[0]['raw'], pri)
+        ONMS.nms_gather(rows, 14, 1000)
+    dt = time.perf_counter() - t0
+    return n_images / dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    per_step = 1                                       # bounded sample: 1 image (T=10) per step, ~0.6 s on 8 cores
+    for _ in range(max(args.warmup, 1)):
+        cpu_oracle_rate(per_step, WORKLOAD['T'], WORKLOAD['img'])
+    t0 = time.perf_counter()
+    cores = 0
+    for _ in range(args.steps):
+        _, cores = cpu_oracle_rate(per_step, WORKLOAD['T'], WORKLOAD['img'])
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    sample = '%d image(s)/step of the same workload (608x608, T=10, decode+NMS), oracle port on %d host threads' % (per_step, cores)
+    print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus,
+                      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+                      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': WORKLOAD,
+                      'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+                      'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--precision', default='fp16')
+    ap.add_argument('--batch', type=int, default=WORKLOAD['batch_per_gpu'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--layers', action='store_true', help='print the per-launch table to stderr')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import byolo
+    from byolo import weights as W
+
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B, T, S, K, Wm = args.batch, WORKLOAD['T'], WORKLOAD['img'], args.steps, max(args.warmup, 3)
+    eng = byolo.Engine('epistemic', (S, S), 2, T=T, max_batch=B, precision=args.precision)
+    eng.load_weights(W.synthetic('epistemic', 2, 0))
+    rng = np.random.default_rng(1000 + rank)
+    n_rot = 4                                           # 4 x 71 MB of images > 126 MB L2: inputs never L2 resident
+    host = [torch.from_numpy(rng.random((B, S, S, 3), dtype=np.float32)).pin_memory() for _ in range(n_rot)]
+    devs = [h.to(dev) for h in host]
+    gathered = torch.empty((world, B, 1000, eng.D), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(i):
+        boxes, cnt, idx = eng.detect(devs[i % n_rot], seed=1003, image_index0=rank * B)
+        if world > 1:                                   # the one exchange of the path: final detections
+            dist.all_gather_into_tensor(gathered, boxes)
+        return boxes, cnt
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(Wm):
+        step(i)
+    barrier()
+    eng.profile(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(K):
+        boxes, cnt = step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = eng.profile_read()
+    eng.profile(False)
+
+    # ---- end to end through the host-buffer entry point (H2D of every step's images, D2H of its detections) ----
+    out = (np.empty((B, 1000, eng.D), np.float32), np.empty((B,), np.int32))
+    for i in range(2):
+        eng.detect_host(host[i % n_rot], seed=1003, image_index0=rank * B, out=out)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        eng.detect_host(host[i % n_rot], seed=1003, image_index0=rank * B, out=out)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak_tf, peak_gbs, peak_src = peaks()
+        conv = [p for p in prof if p['kind'] == 'conv']
+        conv_ms = sum(p['ms'] for p in conv)
+        conv_fl = sum(p['flops'] for p in conv)
+        step_ms = sum(p['ms'] for p in prof)
+        achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        res = {'metric': METRIC, 'value': world * B * K / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': K,
+               'warmup': Wm, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+               'dtype': 'f16' if args.precision != 'fp32' else 'f32', 'data': 'synthetic',
+               'config': dict(WORKLOAD, batch_per_gpu=B, precision=args.precision,
+                              l2='4 rotating input batches (284 MB) > L2; per-step activations (GBs) stream through HBM'),
+               'p50_ms_per_img': ms / K / B,
+               'clocks': clocks,
+               'e2e': {'value': world * B * K / (ms_e2e * 1e-3), 'unit': 'images/s',
+                       'h2d_bytes_per_step': B * S * S * 3 * 4, 'd2h_bytes_per_step': B * 1000 * eng.D * 4 + B * 4},
+               'gpu_launches': eng.launch_count(B) * K,
+               'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (all %d conv launches of a step)' % len(conv),
+                            'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                            'peak_source': peak_src, 'traffic': None, 'conv_share_of_step': conv_ms / step_ms if step_ms else None,
+                            'flops_per_image': eng.flops_per_image(), 'step_tflops': eng.flops_per_image() * B / (ms / K * 1e-3) / 1e12},
+               'breakdown_ms': {k: sum(p['ms'] for p in prof if p['kind'] == k) for k in ('stem', 'conv', 'stack', 'decode', 'nms')}}
+        if args.layers:
+            for p in prof:
+                tf = p['flops'] / (p['ms'] * 1e-3) / 1e12 if p['ms'] > 0 else 0
+                print('%-6s layer %3d  %8.3f ms  %8.1f TFLOP/s' % (p['kind'], p['layer'], p['ms'], tf), file=sys.stderr)
+        if world == 1 and not args.no_cpu_baseline:
+            n_cpu = 8                                   # ~5 s of CPU work on 8 cores
+            v, cores = cpu_oracle_rate(n_cpu, T, S)
+            res['cpu_baseline'] = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                   'sample': '%d images of the same workload (608x608, T=10, decode+NMS) through the oracle '
+                                             'port (torch CPU fp32 + numpy decode + C NMS)' % n_cpu}
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

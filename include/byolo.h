@@ -103,6 +103,13 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
  * order; writes dense fp32 [S,H,W,C] to dst_dev (capacity in floats) and reports the shape.  Valid after a forward. */
 int byolo_get_activation(byolo_handle h, int32_t conv_index, float* dst_dev, size_t capacity, int32_t shape[4], void* stream);
 
+/* Per-launch device timing of byolo_detect (CUDA events on the launch stream).  byolo_profile(h, 1) makes every
+ * following byolo_detect record an event before each launch; byolo_profile_read returns, for the most recent one, one
+ * entry per launch in order: duration [ms], kind (0 stem, 1 conv, 2 MC-stack copy, 3 decode, 4 nms), conv index (or -1)
+ * and that launch's algorithmic FLOPs (2*MAC).  Returns the number of entries.  Waits for the last event. */
+int byolo_profile(byolo_handle h, int32_t enable);
+int byolo_profile_read(byolo_handle h, float* ms, int32_t* kind, int32_t* layer, double* flops, int32_t capacity);
+
 /* Number of kernels one byolo_detect launches for batch B (bench.py reports it as gpu_launches). */
 int byolo_launch_count(byolo_handle h, int32_t B);
 

@@ -113,45 +113,86 @@ int launch_conv_simt(const ConvProblem& p, bool act_half, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------------------
 // K1b: stem conv 3 -> 32, 3x3 stride 1 SAME (darknet.py:10), reading the fp32 image [B,H,W,3] in [0,1) directly
 // (dataset_utils.py:6-11).  K = 27 is too shallow for the tensor pipe; the layer is bound by its 32-channel output.
-// One thread per output pixel: 27 inputs in registers, weights broadcast from shared memory.
 // ------------------------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void st_act16(T* p, const float* v);     // 16 consecutive channels
+template <> __device__ __forceinline__ void st_act16<float>(float* p, const float* v) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+template <> __device__ __forceinline__ void st_act16<__half>(__half* p, const float* v) {
+    uint4 o[2];
+    __half2* h = reinterpret_cast<__half2*>(o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    reinterpret_cast<uint4*>(p)[0] = o[0];
+    reinterpret_cast<uint4*>(p)[1] = o[1];
+}
+
+// One thread = two horizontally adjacent output pixels x 32 channels: 36 input values and 64 accumulators in
+// registers, weights read as broadcast float4 from shared memory (8 FMAs per shared load), 128-byte stores.
 template <typename T>
 __global__ void __launch_bounds__(128)
 stem_kernel(const float* __restrict__ img, int B, int H, int W, const float* __restrict__ w, const float* __restrict__ bias,
             T* __restrict__ out) {
-    __shared__ float sw[27 * 32];
+    __shared__ __align__(16) float sw[27 * 32];
     __shared__ float sb[32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
     if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= (long long)B * H * W) return;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-    float in[27];
+    const int W2 = W >> 1;
+    const long long pid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= (long long)B * H * W2) return;
+    const int x = 2 * (int)(pid % W2), y = (int)((pid / W2) % H), b = (int)(pid / ((long long)W2 * H));
+    float in[3][4][3];                                   // rows y-1..y+1, cols x-1..x+2
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r) {
+        const int iy = y + r - 1;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const int iy = y + r - 1, ix = x + q - 1;
+        for (int q = 0; q < 4; ++q) {
+            const int ix = x + q - 1;
             const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
             const float* p = img + (((long long)b * H + iy) * W + ix) * 3;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) in[(r * 3 + q) * 3 + ch] = ok ? __ldg(p + ch) : 0.f;
+            for (int ch = 0; ch < 3; ++ch) in[r][q][ch] = ok ? __ldg(p + ch) : 0.f;
         }
+    }
     T* o = out + (((long long)b * (H + 2) + y + 1) * (W + 2) + x + 1) * 32;
-#pragma unroll 4
-    for (int c = 0; c < 32; ++c) {
-        float a = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < 27; ++kk) a = fmaf(in[kk], sw[kk * 32 + c], a);
-        a += sb[c];
-        st_act<T>(o + c, fmaxf(a, 0.1f * a));
+    for (int half = 0; half < 2; ++half) {               // 16 output channels at a time keeps the register count down
+        float a0[16], a1[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float v0 = in[r][q][ch], v1 = in[r][q + 1][ch];
+                    const float4* wp = reinterpret_cast<const float4*>(sw + ((r * 3 + q) * 3 + ch) * 32 + half * 16);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 wv = wp[j];
+                        a0[4 * j] = fmaf(v0, wv.x, a0[4 * j]);         a1[4 * j] = fmaf(v1, wv.x, a1[4 * j]);
+                        a0[4 * j + 1] = fmaf(v0, wv.y, a0[4 * j + 1]); a1[4 * j + 1] = fmaf(v1, wv.y, a1[4 * j + 1]);
+                        a0[4 * j + 2] = fmaf(v0, wv.z, a0[4 * j + 2]); a1[4 * j + 2] = fmaf(v1, wv.z, a1[4 * j + 2]);
+                        a0[4 * j + 3] = fmaf(v0, wv.w, a0[4 * j + 3]); a1[4 * j + 3] = fmaf(v1, wv.w, a1[4 * j + 3]);
+                    }
+                }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            a0[c] += sb[half * 16 + c]; a0[c] = fmaxf(a0[c], 0.1f * a0[c]);
+            a1[c] += sb[half * 16 + c]; a1[c] = fmaxf(a1[c], 0.1f * a1[c]);
+        }
+        st_act16<T>(o + half * 16, a0);
+        st_act16<T>(o + 32 + half * 16, a1);
     }
 }
 
 int launch_stem(const float* img, int B, int H, int W, const float* w32, const float* bias, void* out, bool act_half,
                 cudaStream_t st) {
-    const long long total = (long long)B * H * W;
+    BY_REQUIRE(W % 2 == 0, "stem: width must be even");
+    const long long total = (long long)B * H * (W / 2);
     const int grid = (int)((total + 127) / 128);
     if (act_half)
         stem_kernel<__half><<<grid, 128, 0, st>>>(img, B, H, W, w32, bias, (__half*)out);

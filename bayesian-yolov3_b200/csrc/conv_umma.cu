@@ -11,8 +11,8 @@
 //     pixels, loaded with a 4D TMA box over [C, W+2, H+2, S] with element strides (1,2,2,1).
 //   * a 1x1 conv over a channel concat [in1, in2] (route, layers.py:583-592) reads its K range from two maps.
 //
-// Structure: persistent CTAs (one per SM), 256 threads = warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-7 epilogue (TMEM lane quadrant = warp % 4); smem ring of `num_stages` {A,B} tiles with
+// Structure: persistent CTAs (one per SM), 384 threads = warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-11 epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant split the columns); smem ring of `num_stages` {A,B} tiles with
 // full/empty mbarriers; two TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <algorithm>
 #include <cstring>
@@ -87,6 +87,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (tcgen05 "smem descriptor"): start address, stride between 8-row
@@ -101,7 +111,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
     return d;
 }
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;          // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
+constexpr int kMaxBias = 1024;         // floats of BN shift / bias staged in shared memory
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
@@ -113,6 +125,8 @@ struct SmemCtl {
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
     uint32_t tmem_base;
+    uint32_t pad;
+    float bias[kMaxBias];
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -140,7 +154,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&ctl->acc_full[s]), 1);
-            mbar_init(smem_u32(&ctl->acc_empty[s]), 4);
+            mbar_init(smem_u32(&ctl->acc_empty[s]), kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -150,6 +164,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < p.num_n_tiles * p.BN; i += kThreads) ctl->bias[i] = __ldg(p.ep.bias + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -217,9 +232,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
-        const int quad = warp & 3;                       // TMEM lanes [32*quad, 32*quad+32)
+        // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), the two warps of a quadrant interleave the column
+        // chunks.  Per chunk: TMEM -> registers, [dropout] + shift + leaky [+ residual], convert, 16-byte stores.
+        // The residual of chunk i+1 is requested before chunk i is processed (and the first one before the
+        // accumulator barrier), so its L2 latency overlaps TMEM traffic and math.
+        const int quad = warp & 3;
+        const int hsel = (warp - 4) >> 2;
         const Epilogue& ep = p.ep;
         const int Ho = p.gout.H, Wo = p.gout.W;
+        const int CH = (p.BN % 64 == 0) ? 32 : 16;
+        const int nchunks = p.BN / CH;
+        const bool has_res = ep.residual != nullptr;
         uint32_t tile_it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
             const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
@@ -249,39 +272,61 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             const uint32_t elem_pix = (uint32_t)(y * Wo + x) * (uint32_t)ep.cout;      // dropout element index base
             const int t_smp = ep.drop.enabled ? (s % ep.drop.T) : 0;
             const int image = ep.drop.enabled ? (ep.drop.image0 + s / ep.drop.T) : 0;
+            const __half* res_row = reinterpret_cast<const __half*>(ep.residual) + opix_padded * ep.ldc + n0;
+            __half* out_row = reinterpret_cast<__half*>(ep.out) + opix_padded * ep.ldc + n0;
 
+            uint4 rnext[4];
+            if (has_res && valid && hsel < nchunks) {
+                const uint4* rp = reinterpret_cast<const uint4*>(res_row + hsel * CH);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j * 8 < CH) rnext[j] = __ldg(rp + j);
+            }
             mbar_wait(smem_u32(&ctl->acc_full[as]), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quad * 32) << 16);
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                uint32_t raw[16];
-                tmem_ld16(taddr + c0, raw);
+            for (int ch = hsel; ch < nchunks; ch += 2) {
+                const int c0 = ch * CH;                  // column inside the tile
+                uint32_t raw[32];
+                if (CH == 32) tmem_ld32(taddr + c0, raw); else tmem_ld16(taddr + c0, raw);
+                uint4 rcur[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+                if (has_res && valid && ch + 2 < nchunks) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res_row + (ch + 2) * CH);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j * 8 < CH) rnext[j] = __ldg(rp + j);
+                }
                 tmem_ld_wait();
                 const int c = n0 + c0;
                 if (valid && c < ep.cout) {
-                    float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-                    if (ep.drop.enabled) {
-                        dropout8(v, ep.drop, (elem_pix + (uint32_t)c) >> 3, t_smp, image);
-                        dropout8(v + 8, ep.drop, ((elem_pix + (uint32_t)c) >> 3) + 1, t_smp, image);
-                    }
+                    for (int g = 0; g < 2; ++g) {        // two groups of 16 columns (one if CH == 16)
+                        if (g * 16 >= CH) break;
+                        float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] += __ldg(ep.bias + c + j);
-                        if (ep.leaky) v[j] = fmaxf(v[j], 0.1f * v[j]);
-                    }
-                    if (ep.out_mode == OUT_DENSE_F32) {
-                        float* o = reinterpret_cast<float*>(ep.out) + ((long long)(s * Ho + y) * Wo + x) * ep.ldc + c;
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[g * 16 + j]);
+                        const int cg = c + g * 16;
+                        if (ep.drop.enabled) {
+                            dropout8(v, ep.drop, (elem_pix + (uint32_t)cg) >> 3, t_smp, image);
+                            dropout8(v + 8, ep.drop, ((elem_pix + (uint32_t)cg) >> 3) + 1, t_smp, image);
+                        }
+                        const float* bs = ctl->bias + cg;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c + j < ep.cout) o[j] = v[j];
-                    } else {
-                        if (ep.residual) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(ep.residual) +
-                                                                             opix_padded * ep.ldc + c);
-                            uint4 r4[2] = {__ldg(rp), __ldg(rp + 1)};
-                            const __half2* rh = reinterpret_cast<const __half2*>(r4);
+                        for (int j = 0; j < 16; ++j) {
+                            v[j] += bs[j];
+                            if (ep.leaky) v[j] = fmaxf(v[j], 0.1f * v[j]);
+                        }
+                        if (ep.out_mode == OUT_DENSE_F32) {
+                            float* o = reinterpret_cast<float*>(ep.out) + ((long long)(s * Ho + y) * Wo + x) * ep.ldc + cg;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (cg + j < ep.cout) o[j] = v[j];
+                            continue;
+                        }
+                        if (has_res) {
+                            const __half2* rh = reinterpret_cast<const __half2*>(&rcur[g * 2]);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float2 f = __half22float2(rh[j]);
@@ -293,18 +338,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                         __half2* oh = reinterpret_cast<__half2*>(o4);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                        __half* ob = reinterpret_cast<__half*>(ep.out);
                         if (ep.out_mode == OUT_PADDED) {
-                            uint4* o = reinterpret_cast<uint4*>(ob + opix_padded * ep.ldc + c);
+                            uint4* o = reinterpret_cast<uint4*>(out_row + c0 + g * 16);
                             o[0] = o4[0];
                             o[1] = o4[1];
                         } else {   // OUT_UPSAMPLE2: nearest-neighbour x2 -> four destination pixels
+                            __half* ob = reinterpret_cast<__half*>(ep.out);
 #pragma unroll
                             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                                 for (int dx = 0; dx < 2; ++dx) {
                                     const long long q = ((long long)s * (2 * Ho + 2) + (2 * y + dy + 1)) * (2 * Wo + 2) + (2 * x + dx + 1);
-                                    uint4* o = reinterpret_cast<uint4*>(ob + q * ep.ldc + c);
+                                    uint4* o = reinterpret_cast<uint4*>(ob + q * ep.ldc + cg);
                                     o[0] = o4[0];
                                     o[1] = o4[1];
                                 }
@@ -385,7 +430,7 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     BY_REQUIRE(q.stride == 1 || (q.stride == 2 && q.k == 3 && !q.in2), "stride 2 only as the 3x3 downsample conv");
     BY_REQUIRE(!(q.in2 && q.k != 1), "channel-concat input only for 1x1 convs");
     BY_REQUIRE(C1 % 32 == 0 && C2 % 32 == 0, "channel counts must be multiples of 32");
-    BY_REQUIRE(q.cout_pad % 16 == 0, "padded cout must be a multiple of 16");
+    BY_REQUIRE(q.cout_pad % 16 == 0 && q.cout_pad <= kMaxBias, "padded cout must be a multiple of 16 and <= 1024");
     p.BK = (C1 % 64 == 0 && C2 % 64 == 0) ? 64 : 32;
     p.taps = q.k * q.k;
     p.kb1 = C1 / p.BK;

@@ -43,9 +43,9 @@ struct Geom {
 };
 
 enum OutMode : int {
-    OUT_PADDED = 0,      // T  [S,H+2,W+2,ldc]   same geometry as the (stride-1) input
-    OUT_DENSE_F32 = 1,   // f32 [S,H,W,ldc]       detection conv -> raw head output
-    OUT_UPSAMPLE2 = 2,   // T  [S,2H+2,2W+2,ldc]  nearest x2 (layers.py:578-580) fused into the store
+    OUT_PADDED = 0,      // T   [S,H+2,W+2,ldc]   same geometry as the (stride-1) input
+    OUT_PADDED_F32 = 1,  // f32 [S,H+2,W+2,ldc]   detection conv -> raw head output, ldc = cout padded to 16
+    OUT_UPSAMPLE2 = 2,   // T   [S,2H+2,2W+2,ldc] nearest x2 (layers.py:578-580) fused into the store
 };
 
 struct Dropout {
@@ -126,8 +126,9 @@ struct DecodeProblem {
     int B, T;                // images, samples per image (1 unless epistemic)
     int cls_cnt;
     int gh[3], gw[3];        // grids, stride 32/16/8
-    const float* raw[3];     // [B*T, gh, gw, ld]  dense fp32
+    const float* raw[3];     // [B*T, gh(+2), gw(+2), ld] fp32; padded = 1: one-pixel border around each map (engine layout)
     int ld[3];
+    int padded;
     float prior_h[9], prior_w[9];
     float* rows;             // [B, N, D]
     int N, D;

@@ -77,8 +77,8 @@ conv_simt_kernel(const T* __restrict__ in1, const T* __restrict__ in2, Geom g, i
         if (c + j >= ep.cout) break;
         float v = acc[j] + __ldg(ep.bias + c + j);
         if (ep.leaky) v = fmaxf(v, 0.1f * v);
-        if (ep.out_mode == OUT_DENSE_F32) {
-            reinterpret_cast<float*>(ep.out)[((long long)(s * Ho + y) * Wo + x) * ep.ldc + c + j] = v;
+        if (ep.out_mode == OUT_PADDED_F32) {
+            reinterpret_cast<float*>(ep.out)[opix * ep.ldc + c + j] = v;
             continue;
         }
         if (ep.residual) v += ld_act<T>(reinterpret_cast<const T*>(ep.residual) + opix * ep.ldc + c + j);

@@ -62,6 +62,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -114,6 +123,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 constexpr int kThreads = 384;          // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
 constexpr int kMaxBias = 1024;         // floats of BN shift / bias staged in shared memory
+constexpr int kStageOutBytes = 2048;   // per epilogue warp: 32 rows x 64 B output chunk for the TMA store
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
@@ -131,12 +141,14 @@ struct SmemCtl {
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
-                 const __grid_constant__ CUtensorMap map_b, const UmmaParams p) {
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o, const UmmaParams p) {
     extern __shared__ uint8_t smem_raw[];
-    // ring of {A,B} tiles, 1024B aligned (SWIZZLE_128B atoms are 1024B); control block behind it
+    // ring of {A,B} tiles, 1024B aligned (SWIZZLE_128B atoms are 1024B); output staging and control block behind it
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (ring - smem_u32(smem_raw)) + (size_t)p.num_stages * stage_bytes);
+    const uint32_t out_stage = ring + p.num_stages * stage_bytes;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (ring - smem_u32(smem_raw)) + (size_t)p.num_stages * stage_bytes +
+                                              kEpiWarps * kStageOutBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -146,6 +158,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_a2);
         tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_o);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.num_stages; ++s) {
@@ -233,16 +246,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     } else if (warp >= 4) {
         // ================================ epilogue ================================
         // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), the two warps of a quadrant interleave the column
-        // chunks.  Per chunk: TMEM -> registers, [dropout] + shift + leaky [+ residual], convert, 16-byte stores.
-        // The residual of chunk i+1 is requested before chunk i is processed (and the first one before the
-        // accumulator barrier), so its L2 latency overlaps TMEM traffic and math.
+        // chunks.  A chunk is 64 bytes of output per row (32 fp16 or 16 fp32 columns): TMEM -> registers,
+        // [dropout] + shift + leaky [+ residual], convert, then
+        //   * stride-1 layers: the warp's 32 x 64 B block goes to 64B-swizzled shared memory and out with one TMA
+        //     store (rows that are border pixels are written as zeros, which is what the border holds anyway);
+        //   * stride-2 / upsampling layers: 16-byte stores straight from registers (rows are not contiguous there).
+        // The residual of the next chunk is requested before the current one is processed (the first one before the
+        // accumulator barrier), so its latency overlaps TMEM traffic and math.
         const int quad = warp & 3;
         const int hsel = (warp - 4) >> 2;
         const Epilogue& ep = p.ep;
         const int Ho = p.gout.H, Wo = p.gout.W;
-        const int CH = (p.BN % 64 == 0) ? 32 : 16;
+        const bool f32out = ep.out_mode == OUT_PADDED_F32;
+        const bool tma_out = !p.s2 && ep.out_mode != OUT_UPSAMPLE2;
+        const int CH = f32out ? 16 : 32;
         const int nchunks = p.BN / CH;
         const bool has_res = ep.residual != nullptr;
+        const uint32_t stg = out_stage + (uint32_t)(warp - 4) * kStageOutBytes;
+        const uint32_t stg_row = stg + lane * 64;
+        const uint32_t swz = (uint32_t)((lane >> 1) & 3);
         uint32_t tile_it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
             const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
@@ -273,14 +295,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             const int t_smp = ep.drop.enabled ? (s % ep.drop.T) : 0;
             const int image = ep.drop.enabled ? (ep.drop.image0 + s / ep.drop.T) : 0;
             const __half* res_row = reinterpret_cast<const __half*>(ep.residual) + opix_padded * ep.ldc + n0;
-            __half* out_row = reinterpret_cast<__half*>(ep.out) + opix_padded * ep.ldc + n0;
 
             uint4 rnext[4];
             if (has_res && valid && hsel < nchunks) {
                 const uint4* rp = reinterpret_cast<const uint4*>(res_row + hsel * CH);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (j * 8 < CH) rnext[j] = __ldg(rp + j);
+                for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
             }
             mbar_wait(smem_u32(&ctl->acc_full[as]), aphase);
             tc_fence_after();
@@ -288,43 +308,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             for (int ch = hsel; ch < nchunks; ch += 2) {
                 const int c0 = ch * CH;                  // column inside the tile
                 uint32_t raw[32];
-                if (CH == 32) tmem_ld32(taddr + c0, raw); else tmem_ld16(taddr + c0, raw);
+                if (f32out) tmem_ld16(taddr + c0, raw); else tmem_ld32(taddr + c0, raw);
                 uint4 rcur[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
                 if (has_res && valid && ch + 2 < nchunks) {
                     const uint4* rp = reinterpret_cast<const uint4*>(res_row + (ch + 2) * CH);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j * 8 < CH) rnext[j] = __ldg(rp + j);
+                    for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
                 }
                 tmem_ld_wait();
                 const int c = n0 + c0;
-                if (valid && c < ep.cout) {
+                uint4 o4[4];                             // the 64 output bytes of this row
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {        // two groups of 16 columns (one if CH == 16)
-                        if (g * 16 >= CH) break;
-                        float v[16];
+                for (int g = 0; g < 2; ++g) {            // groups of 16 accumulator columns (one group if fp32 output)
+                    if (g == 1 && f32out) break;
+                    float v[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[g * 16 + j]);
-                        const int cg = c + g * 16;
-                        if (ep.drop.enabled) {
-                            dropout8(v, ep.drop, (elem_pix + (uint32_t)cg) >> 3, t_smp, image);
-                            dropout8(v + 8, ep.drop, ((elem_pix + (uint32_t)cg) >> 3) + 1, t_smp, image);
-                        }
-                        const float* bs = ctl->bias + cg;
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[g * 16 + j]);
+                    const int cg = c + g * 16;
+                    if (ep.drop.enabled) {
+                        dropout8(v, ep.drop, (elem_pix + (uint32_t)cg) >> 3, t_smp, image);
+                        dropout8(v + 8, ep.drop, ((elem_pix + (uint32_t)cg) >> 3) + 1, t_smp, image);
+                    }
+                    const float* bs = ctl->bias + cg;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            v[j] += bs[j];
-                            if (ep.leaky) v[j] = fmaxf(v[j], 0.1f * v[j]);
-                        }
-                        if (ep.out_mode == OUT_DENSE_F32) {
-                            float* o = reinterpret_cast<float*>(ep.out) + ((long long)(s * Ho + y) * Wo + x) * ep.ldc + cg;
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] += bs[j];
+                        if (ep.leaky) v[j] = fmaxf(v[j], 0.1f * v[j]);
+                    }
+                    if (f32out) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (cg + j < ep.cout) o[j] = v[j];
-                            continue;
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            o4[j] = valid ? make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]))
+                                          : make_uint4(0u, 0u, 0u, 0u);
+                    } else {
                         if (has_res) {
                             const __half2* rh = reinterpret_cast<const __half2*>(&rcur[g * 2]);
 #pragma unroll
@@ -334,26 +353,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                                 v[2 * j + 1] += f.y;
                             }
                         }
-                        uint4 o4[2];
-                        __half2* oh = reinterpret_cast<__half2*>(o4);
+                        __half2* oh = reinterpret_cast<__half2*>(&o4[g * 2]);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                        if (ep.out_mode == OUT_PADDED) {
-                            uint4* o = reinterpret_cast<uint4*>(out_row + c0 + g * 16);
-                            o[0] = o4[0];
-                            o[1] = o4[1];
-                        } else {   // OUT_UPSAMPLE2: nearest-neighbour x2 -> four destination pixels
-                            __half* ob = reinterpret_cast<__half*>(ep.out);
+                        for (int j = 0; j < 8; ++j) oh[j] = valid ? __floats2half2_rn(v[2 * j], v[2 * j + 1]) : __floats2half2_rn(0.f, 0.f);
+                    }
+                }
+                if (tma_out) {
+                    if (lane == 0) bulk_wait_read0();    // the previous store of this warp has drained the staging block
+                    __syncwarp();
 #pragma unroll
-                            for (int dy = 0; dy < 2; ++dy)
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t dst = stg_row + (((uint32_t)j ^ swz) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o4[j].x), "r"(o4[j].y), "r"(o4[j].z),
+                                     "r"(o4[j].w)
+                                     : "memory");
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_o, stg, c, m_tile * kTileM + quad * 32);
+                        bulk_commit();
+                    }
+                } else if (valid) {
+                    __half* ob = reinterpret_cast<__half*>(ep.out);
+                    if (ep.out_mode == OUT_PADDED) {
+                        uint4* o = reinterpret_cast<uint4*>(ob + opix_padded * ep.ldc + c);
 #pragma unroll
-                                for (int dx = 0; dx < 2; ++dx) {
-                                    const long long q = ((long long)s * (2 * Ho + 2) + (2 * y + dy + 1)) * (2 * Wo + 2) + (2 * x + dx + 1);
-                                    uint4* o = reinterpret_cast<uint4*>(ob + q * ep.ldc + cg);
-                                    o[0] = o4[0];
-                                    o[1] = o4[1];
-                                }
-                        }
+                        for (int j = 0; j < 4; ++j) o[j] = o4[j];
+                    } else {   // OUT_UPSAMPLE2: nearest-neighbour x2 -> four destination pixels
+#pragma unroll
+                        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const long long q = ((long long)s * (2 * Ho + 2) + (2 * y + dy + 1)) * (2 * Wo + 2) + (2 * x + dx + 1);
+                                uint4* o = reinterpret_cast<uint4*>(ob + q * ep.ldc + c);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) o[j] = o4[j];
+                            }
                     }
                 }
             }
@@ -361,6 +397,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty[as]));
         }
+        if (tma_out && lane == 0) bulk_wait0();          // all output writes complete before the CTA retires
     }
 
     // ---------------- teardown ----------------
@@ -390,14 +427,14 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, const uint32_t* estr, int swizzle_bytes) {
+                    const uint32_t* box, const uint32_t* estr, int swizzle_bytes, bool f32 = false) {
     EncodeTiledFn fn = encode_fn();
     BY_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t d[5], s[4];
     cuuint32_t b[5], e[5];
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = estr[i]; }
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
+    CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -444,7 +481,8 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.gout.H = g.H / q.stride;
     p.gout.W = g.W / q.stride;
     p.gout.C = q.ep.cout;
-    if (q.ep.out_mode != OUT_DENSE_F32) BY_REQUIRE(q.ep.cout % 16 == 0 && q.ep.ldc % 8 == 0, "fp16 outputs need cout % 16 == 0");
+    if (q.ep.out_mode != OUT_PADDED_F32) BY_REQUIRE(q.ep.cout % 32 == 0 && q.ep.ldc % 32 == 0, "fp16 outputs need cout % 32 == 0");
+    else BY_REQUIRE(q.ep.ldc == q.cout_pad && !p.s2, "fp32 (detection) outputs are stored cout_pad wide, stride 1 only");
     p.ep = q.ep;
     const int swz = p.BK * 2;                                     // 128B or 64B rows
     p.sbo_bytes = 8 * swz;
@@ -453,9 +491,9 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.b_bytes = p.BN * swz;
     // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     p.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    const int budget = 227 * 1024 - 1024 - (int)sizeof(SmemCtl) - 64;
+    const int budget = 227 * 1024 - 1024 - (int)sizeof(SmemCtl) - kEpiWarps * kStageOutBytes - 64;
     p.num_stages = std::max(2, std::min(kMaxStages, budget / (p.a_bytes + p.b_bytes)));
-    L->smem_bytes = p.num_stages * (p.a_bytes + p.b_bytes) + 1024 + sizeof(SmemCtl) + 64;
+    L->smem_bytes = p.num_stages * (p.a_bytes + p.b_bytes) + 1024 + sizeof(SmemCtl) + kEpiWarps * kStageOutBytes + 64;
 
     const uint32_t one[5] = {1, 1, 1, 1, 1};
     if (!p.s2) {
@@ -488,6 +526,15 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
         uint32_t box[2] = {(uint32_t)p.BK, (uint32_t)p.BN};
         if (int e = make_map(&L->b, q.w16, 2, d, s, box, one, swz)) return e;
     }
+    L->o = L->b;
+    if (!p.s2 && q.ep.out_mode != OUT_UPSAMPLE2) {
+        // output map: [rows, ldc] of the padded output buffer (same row indexing as the A operand), 32 x 64 B boxes
+        const bool f32 = q.ep.out_mode == OUT_PADDED_F32;
+        const long long rows = g.rows();
+        uint64_t d[2] = {(uint64_t)q.ep.ldc, (uint64_t)rows}, st[1] = {(uint64_t)q.ep.ldc * (f32 ? 4 : 2)};
+        uint32_t box[2] = {(uint32_t)(f32 ? 16 : 32), 32u};
+        if (int e = make_map(&L->o, q.ep.out, 2, d, st, box, one, 64, f32)) return e;
+    }
     p.num_tiles = p.num_m_tiles * p.num_n_tiles;
     int dev = 0, sms = 0;
     BY_CUDA(cudaGetDevice(&dev));
@@ -503,7 +550,7 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
 }
 
 int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
-    conv_umma_kernel<<<L.grid, kThreads, L.smem_bytes, st>>>(L.a1, L.a2, L.b, L.p);
+    conv_umma_kernel<<<L.grid, kThreads, L.smem_bytes, st>>>(L.a1, L.a2, L.b, L.o, L.p);
     BY_CUDA(cudaGetLastError());
     return 0;
 }

@@ -20,7 +20,7 @@ struct UmmaParams {
 };
 
 struct UmmaLaunch {
-    CUtensorMap a1, a2, b;
+    CUtensorMap a1, a2, b, o;
     UmmaParams p;
     int grid;
     int smem_bytes;

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeProblem p) {
         if (a < n) break;
         a -= n;
     }
-    const int lh = p.gh[j], lw = p.gw[j];
+    const int lh = p.gh[j], lw = p.gw[j], pad = p.padded;
     const int prior = a / (lh * lw);
     const int cell = a - prior * lh * lw;
     const int row = cell / lw, col = cell - row * lw;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeProblem p) {
     float tx, ty, tw, th;      // (mean) t-space location
 
     if (p.variant != 2) {
-        const float* v = p.raw[j] + ((long long)(b * lh + row) * lw + col) * p.ld[j] + prior * block;
+        const float* v = p.raw[j] + ((long long)(b * (lh + 2 * pad) + row + pad) * (lw + 2 * pad) + col + pad) * p.ld[j] + prior * block;
         tx = v[0]; ty = v[1]; tw = v[2]; th = v[3];
         float cls[kMaxCls];
         if (p.variant == 0) {
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeProblem p) {
             for (int k = 0; k < 4; ++k) s_out[i][k] = 0.f;
         for (int i = 0; i < C; ++i) s_cls[i] = 0.f;
         for (int t = 0; t < T; ++t) {
-            const float* v = p.raw[j] + ((long long)((b * T + t) * lh + row) * lw + col) * p.ld[j] + prior * block;
+            const float* v = p.raw[j] + ((long long)((b * T + t) * (lh + 2 * pad) + row + pad) * (lw + 2 * pad) + col + pad) * p.ld[j] + prior * block;
             float loc[4];
             for (int i = 0; i < 4; ++i) { loc[i] = v[i]; s_loc[i] += loc[i]; s_var[i] += expf(v[4 + i]); }
             for (int i = 0; i < 4; ++i)

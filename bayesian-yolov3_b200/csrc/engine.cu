@@ -95,8 +95,9 @@ static int fold_and_upload(const LayerDef& d, const float* kernel, const float* 
 
 struct Buffer {
     void* ptr = nullptr;
-    Geom g{0, 0, 0, 0};
-    bool dense_f32 = false;
+    Geom g{0, 0, 0, 0};            // padded-NHWC geometry; C = stored channels
+    bool f32 = false;              // raw detection maps are fp32 (C = cout padded to 16), everything else is T
+    int valid_c = 0;               // channels that carry data (== C except for the raw detection maps)
     size_t bytes = 0;
 };
 
@@ -160,11 +161,12 @@ struct byolo_engine {
 
 namespace byolo {
 
-static int new_buffer(byolo_engine* e, Plan* pl, int S, int H, int W, int C, bool dense_f32, int* id) {
+static int new_buffer(byolo_engine* e, Plan* pl, int S, int H, int W, int C, bool f32, int* id) {
     Buffer b;
     b.g = Geom{S, H, W, C};
-    b.dense_f32 = dense_f32;
-    b.bytes = dense_f32 ? (size_t)S * H * W * C * 4 : (size_t)b.g.rows() * C * e->esize();
+    b.f32 = f32;
+    b.valid_c = C;
+    b.bytes = (size_t)b.g.rows() * C * (f32 ? 4 : e->esize());
     BY_CUDA(cudaMalloc(&b.ptr, b.bytes));
     BY_CUDA(cudaMemset(b.ptr, 0, b.bytes));      // padded buffers: the border is written exactly once, here
     pl->bufs.push_back(b);
@@ -180,8 +182,9 @@ static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int res
     BY_REQUIRE(bin.g.C + (in2 >= 0 ? pl->bufs[in2].g.C : 0) == d.cin, "plan wiring: channel mismatch");
     const int Ho = bin.g.H / d.s, Wo = bin.g.W / d.s;
     int ob;
-    if (out_mode == OUT_DENSE_F32) {
-        if (int r = new_buffer(e, pl, bin.g.S, Ho, Wo, d.cout, true, &ob)) return r;
+    if (out_mode == OUT_PADDED_F32) {
+        if (int r = new_buffer(e, pl, bin.g.S, Ho, Wo, w.cout_pad, true, &ob)) return r;
+        pl->bufs[ob].valid_c = d.cout;
     } else if (out_mode == OUT_UPSAMPLE2) {
         if (int r = new_buffer(e, pl, bin.g.S, 2 * Ho, 2 * Wo, d.cout, false, &ob)) return r;
     } else {
@@ -205,7 +208,7 @@ static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int res
     p.ep.residual = residual >= 0 ? pl->bufs[residual].ptr : nullptr;
     p.ep.out = pl->bufs[ob].ptr;
     p.ep.out_mode = out_mode;
-    p.ep.ldc = d.cout;
+    p.ep.ldc = out_mode == OUT_PADDED_F32 ? w.cout_pad : d.cout;
     p.ep.cout = d.cout;
     p.ep.leaky = d.bn;
     p.ep.drop.enabled = drop_id >= 0;
@@ -285,7 +288,7 @@ static int build_plan(byolo_engine* e, int B, Plan* pl) {
             if (int r = add_conv(e, pl, l, x, (i == 0) ? x2 : -1, -1, OUT_PADDED, drop_id(l), &x)) return r;
             if (i == 4) c5 = x;
         }
-        if (int r = add_conv(e, pl, li++, x, -1, -1, OUT_DENSE_F32, -1, &pl->raw_buf[j])) return r;   // detection conv
+        if (int r = add_conv(e, pl, li++, x, -1, -1, OUT_PADDED_F32, -1, &pl->raw_buf[j])) return r;  // detection conv
         route_src = c5;                                                                            // route([-3])
     }
     BY_REQUIRE(li == (int)e->layers.size(), "plan did not consume all layers");
@@ -344,6 +347,7 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
         dp.raw[j] = (const float*)pl->bufs[pl->raw_buf[j]].ptr;
         dp.ld[j] = pl->bufs[pl->raw_buf[j]].g.C;
     }
+    dp.padded = 1;
     for (int i = 0; i < 9; ++i) { dp.prior_h[i] = c.prior_h[i]; dp.prior_w[i] = c.prior_w[i]; }
     dp.rows = rows;
     dp.N = e->N;
@@ -543,6 +547,7 @@ int byolo_decode(byolo_handle h, const float* raw0_dev, const float* raw1_dev, c
     const float* raws[3] = {raw0_dev, raw1_dev, raw2_dev};
     const int det_ch = h->layers.back().cout;
     for (int j = 0; j < 3; ++j) { dp.gh[j] = h->gh[j]; dp.gw[j] = h->gw[j]; dp.raw[j] = raws[j]; dp.ld[j] = det_ch; }
+    dp.padded = 0;
     for (int i = 0; i < 9; ++i) { dp.prior_h[i] = c.prior_h[i]; dp.prior_w[i] = c.prior_w[i]; }
     dp.rows = rows_dev;
     dp.N = h->N;
@@ -568,7 +573,8 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
     const Geom g1{S, H, W, cin1}, g2{S, H, W, cin2};
     const int Ho = H / stride, Wo = W / stride;
     const bool dense = bn_host == nullptr;
-    const Geom go{S, upsample ? 2 * Ho : Ho, upsample ? 2 * Wo : Wo, cout};
+    const Geom go{S, upsample ? 2 * Ho : Ho, upsample ? 2 * Wo : Wo, dense ? w.cout_pad : cout};
+    float* tmp = nullptr;          // dense path: un-padded but still cout_pad wide
     auto alloc0 = [&](void** p, size_t bytes) {
         if (rc) return;
         if (cudaMalloc(p, bytes) != cudaSuccess || cudaMemsetAsync(*p, 0, bytes, st) != cudaSuccess) {
@@ -579,7 +585,8 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
     alloc0(&p1, (size_t)g1.rows() * cin1 * es);
     if (in2_dev) alloc0(&p2, (size_t)g2.rows() * cin2 * es);
     if (residual_dev) alloc0(&pr, (size_t)go.rows() * cout * es);
-    alloc0(&po, dense ? (size_t)S * Ho * Wo * cout * 4 : (size_t)go.rows() * cout * es);
+    alloc0(&po, (size_t)go.rows() * go.C * (dense ? 4 : es));
+    if (dense) alloc0((void**)&tmp, (size_t)S * Ho * Wo * go.C * 4);
     if (!rc) rc = launch_pack(in1_dev, p1, g1, half, st);
     if (!rc && in2_dev) rc = launch_pack(in2_dev, p2, g2, half, st);
     if (!rc && residual_dev) rc = launch_pack(residual_dev, pr, go, half, st);
@@ -588,8 +595,8 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
         p.in1 = p1; p.in2 = p2; p.gin = g1; p.c2 = cin2; p.k = k; p.stride = stride;
         p.cout_pad = w.cout_pad; p.w16 = w.w16; p.w32 = w.w32;
         p.ep.bias = w.bias; p.ep.residual = pr; p.ep.out = po;
-        p.ep.out_mode = dense ? OUT_DENSE_F32 : (upsample ? OUT_UPSAMPLE2 : OUT_PADDED);
-        p.ep.ldc = cout; p.ep.cout = cout; p.ep.leaky = d.bn;
+        p.ep.out_mode = dense ? OUT_PADDED_F32 : (upsample ? OUT_UPSAMPLE2 : OUT_PADDED);
+        p.ep.ldc = go.C; p.ep.cout = cout; p.ep.leaky = d.bn;
         p.ep.drop.enabled = dropout_layer >= 0;
         p.ep.drop.layer_id = dropout_layer; p.ep.drop.T = T > 0 ? T : 1; p.ep.drop.image0 = image_index0;
         p.ep.drop.seed_lo = (uint32_t)seed; p.ep.drop.seed_hi = (uint32_t)(seed >> 32);
@@ -599,7 +606,10 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
     }
     if (!rc) {
         if (dense) {
-            if (cudaMemcpyAsync(out_dev, po, (size_t)S * Ho * Wo * cout * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = -2;
+            rc = launch_unpack(po, tmp, go, false, st);
+            if (!rc && cudaMemcpy2DAsync(out_dev, (size_t)cout * 4, tmp, (size_t)go.C * 4, (size_t)cout * 4, (size_t)S * Ho * Wo,
+                                         cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+                rc = -2;
         } else {
             rc = launch_unpack(po, out_dev, go, half, st);
         }
@@ -609,6 +619,7 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
         set_error(std::string("byolo_conv_layer: ") + cudaGetErrorString(se));
         rc = -2;
     }
+    cudaFree(tmp);
     cudaFree(p1); cudaFree(p2); cudaFree(pr); cudaFree(po);
     w.release();
     return rc;
@@ -620,14 +631,22 @@ int byolo_get_activation(byolo_handle h, int32_t conv_index, float* dst_dev, siz
     Plan* pl = h->last_plan;
     BY_REQUIRE(conv_index >= 0 && conv_index < (int)pl->conv_out.size(), "conv index out of range");
     const Buffer& b = pl->bufs[pl->conv_out[conv_index]];
-    shape[0] = b.g.S; shape[1] = b.g.H; shape[2] = b.g.W; shape[3] = b.g.C;
-    const size_t n = (size_t)b.g.S * b.g.H * b.g.W * b.g.C;
+    shape[0] = b.g.S; shape[1] = b.g.H; shape[2] = b.g.W; shape[3] = b.valid_c;
+    const size_t n = (size_t)b.g.S * b.g.H * b.g.W * b.valid_c;
     BY_REQUIRE(capacity >= n, "destination too small");
-    if (b.dense_f32) {
-        BY_CUDA(cudaMemcpyAsync(dst_dev, b.ptr, n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-        return 0;
-    }
-    return launch_unpack(b.ptr, dst_dev, b.g, h->act_half(), (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!b.f32) return launch_unpack(b.ptr, dst_dev, b.g, h->act_half(), st);
+    // raw detection map: fp32, stored cout_pad wide -> un-pad, then drop the padding channels
+    float* tmp = nullptr;
+    const size_t pix = (size_t)b.g.S * b.g.H * b.g.W;
+    BY_CUDA(cudaMalloc(&tmp, pix * b.g.C * 4));
+    int rc = launch_unpack(b.ptr, tmp, b.g, false, st);
+    if (!rc && cudaMemcpy2DAsync(dst_dev, (size_t)b.valid_c * 4, tmp, (size_t)b.g.C * 4, (size_t)b.valid_c * 4, pix,
+                                 cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        rc = -2;
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return rc;
 }
 
 int byolo_launch_count(byolo_handle h, int32_t B) {

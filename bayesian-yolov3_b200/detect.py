@@ -1,0 +1,142 @@
+"""Single-image detection with the same call surface as the reference's detect.py: box_op_*, filter_boxes,
+preproces_boxes, draw_boxes, load_img, load_model(sess, config, model_cls), do_it(...), main().
+The model runs in libbyolo; `sess` is the byolo.compat.Session stand-in."""
+import glob
+import logging
+import os
+
+import numpy as np
+
+import inference_aleatoric
+import inference_epistemic
+import inference_standard_yolov3
+from byolo import compat as tf
+from byolo import ecp
+from lib_yolo import yolov3
+
+
+def box_op_standard(model):
+    bbox = inference_standard_yolov3.concat_bbox(model.det_layers, model=model)
+    return inference_standard_yolov3.nms(bbox, model)[0, ...]
+
+
+def box_op_aleatoric(model):
+    bbox = inference_aleatoric.concat_bbox(model.det_layers, model=model)
+    return inference_aleatoric.nms(bbox, model)[0, ...]
+
+
+def box_op_bayes(model):
+    bbox = inference_epistemic.concat_bbox(model.det_layers, model=model)
+    return inference_epistemic.nms(bbox, model)
+
+
+def filter_boxes(boxes, obj_idx, thresh):
+    return [box for box in boxes if box[obj_idx] > thresh]
+
+
+def preproces_boxes(img_size, boxes, obj_idx, cls_start_idx, cls_cnt, config, cls_mapping=None):
+    out = []
+    for box in boxes:
+        cls_idx = np.argmax(box[cls_start_idx:cls_start_idx + cls_cnt])
+        if config['implicit_background_class']:
+            cls_idx += 1
+        cls = cls_mapping[cls_idx] if cls_mapping else cls_idx
+        # as written in the reference (detect.py:51): indexed AFTER the +1 background shift
+        cls_score = box[cls_idx + cls_start_idx]
+        y0, x0, y1, x1 = (np.clip(box[i], 0, 1) * img_size[i % 2] for i in range(4))
+        out.append({'cls': cls, 'score': box[obj_idx] * cls_score, 'obj_score': box[obj_idx], 'cls_score': cls_score,
+                    'y0': y0, 'x0': x0, 'y1': y1, 'x1': x1})
+    return out
+
+
+def draw_boxes(img, boxes, color=(43, 219, 216), thickness=1):
+    import cv2
+    color = np.array(color) / 255.
+    for box in boxes:
+        text = '{} {:4.3f}'.format(box['cls'], box['score'])
+        cv2.putText(img, text, (int(box['x0']), int(box['y0'])), cv2.FONT_HERSHEY_SIMPLEX, 0.5, color, thickness)
+        cv2.rectangle(img, (int(box['x0']), int(box['y0'])), (int(box['x1']), int(box['y1'])), color, thickness)
+
+
+def load_img(config, img_size, filename):
+    """float32 RGB in [0,1], centre-cropped when config['crop'], with a leading batch axis (detect.py:76-85)."""
+    if filename.endswith('.npy'):
+        img = np.load(filename).astype(np.float32)
+    else:
+        import cv2
+        img = cv2.imread(filename, cv2.IMREAD_COLOR)[:, :, ::-1].astype(np.float32) / np.float32(255.0)
+    if config['crop']:
+        y = (img.shape[0] - img_size[0]) // 2
+        x = (img.shape[1] - img_size[1]) // 2
+        img = img[y:y + img_size[0], x:x + img_size[1], :]
+    return np.expand_dims(np.ascontiguousarray(img), axis=0)
+
+
+def load_model(sess, config, model_cls):
+    if model_cls == yolov3.bayesian_yolov3_aleatoric:
+        config['inference_mode'] = True
+    yolo = model_cls(config)
+    img_tensor = tf.Placeholder(shape=(1, *yolo.img_size))
+    weights, _ = ecp.find_weights(config)
+    yolo.load_weights(weights)
+    model = yolo.init_model(inputs=img_tensor, training=False).get_model()
+    return model, img_tensor
+
+
+def do_it(files, thresh, config, model_cls, cls_mapping, show=False):
+    box_op = {yolov3.yolov3: box_op_standard, yolov3.yolov3_aleatoric: box_op_aleatoric,
+              yolov3.bayesian_yolov3_aleatoric: box_op_bayes}[model_cls]
+    results = {}
+    with tf.Session(seed=config.get('seed', 0)) as sess:
+        model, img_tensor = load_model(sess, config, model_cls)
+        img_size = img_tensor.shape.as_list()[1:]
+        op = box_op(model)                                    # built once (the reference re-adds it per file)
+        for file in files:
+            img = load_img(config, img_size, file)
+            boxes, = sess.run([op], feed_dict={img_tensor: img})
+            if model.variant != 'epistemic':
+                boxes = boxes[:sess.last_counts[0]]
+            boxes = filter_boxes(boxes, model.obj_idx, thresh)
+            boxes = preproces_boxes(img_size, boxes, model.obj_idx, model.cls_start_idx, model.cls_cnt, config,
+                                    cls_mapping=cls_mapping)
+            img = img[0, ...]
+            draw_boxes(img, boxes)
+            logging.info('{}: {}'.format(os.path.basename(file), boxes))
+            results[file] = boxes
+            if show:                                          # interactive display is out of scope; save instead
+                import cv2
+                os.makedirs(config['out_path'], exist_ok=True)
+                cv2.imwrite(os.path.join(config['out_path'], os.path.basename(file) + '.det.png'),
+                            (np.clip(img[:, :, ::-1], 0, 1) * 255).astype(np.uint8))
+    return results
+
+
+def main():
+    config = {
+        'checkpoint_path': './checkpoints/',
+        'run_id': 'epi_ale',  # edit
+        'step': 'last',  # edit: int or 'last'
+        'crop_img_size': [768, 1440, 3],
+        'full_img_size': [1024, 1920, 3],  # edit if not ecp
+        'cls_cnt': 2,  # edit if not ecp
+        'T': 35,  # only relevant for bayesian model
+        'cpu_thread_cnt': 10,
+        'freeze_darknet53': False,
+        'crop': False,
+        'training': False,
+        'aleatoric_loss': True,
+        'priors': yolov3.ECP_9_PRIORS,
+        'out_path': './uncertainty_visualization',  # edit
+        'implicit_background_class': True,  # whether the label ids start at 1 or 0. True = 1, False = 0
+    }
+    cls_mapping = {1: 'ped', 2: 'rider'}  # edit; {0: 'ped', 1: 'rider'} if labels start at 0
+    thresh = 0.1  # edit
+    files = glob.glob('./test_images/*')  # edit
+    model_cls = yolov3.bayesian_yolov3_aleatoric  # edit: yolov3.yolov3 | yolov3.yolov3_aleatoric
+    do_it(files, thresh, config, model_cls, cls_mapping, show=True)
+
+
+if __name__ == '__main__':
+    logging.basicConfig(level=logging.DEBUG, format='%(asctime)s, pid: %(process)d, %(levelname)-8s %(message)s',
+                        datefmt='%a, %d %b %Y %H:%M:%S')
+    main()

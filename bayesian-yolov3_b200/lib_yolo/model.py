@@ -1,0 +1,91 @@
+"""Containers the reference's scripts read from a built model (reference: lib_yolo/model.py:188-268).
+The graph builder itself (ModelBuilder, model.py:20-185) is replaced by the execution plan inside libbyolo."""
+import numpy as np
+
+from byolo.priors import Prior
+
+
+def img_size_and_priors_if_crop(config):
+    """model.py:6-17.  Returns (img_size, priors); priors are rescaled when cropping.  Unlike the reference this does
+    not write the rescaled priors back into config['priors'] (the reference mutates the shared module-level table)."""
+    img_size = config['crop_img_size'] if config.get('crop') else config['full_img_size']
+    priors = config['priors']
+    if config.get('crop'):
+        sh = config['full_img_size'][0] / float(config['crop_img_size'][0])
+        sw = config['full_img_size'][1] / float(config['crop_img_size'][1])
+        priors = {s: [Prior(h=p.h * sh, w=p.w * sw) for p in prs] for s, prs in priors.items()}
+    return img_size, priors
+
+
+class DetLayerBlueprint:
+    def __init__(self, input_img_size, downsample_factor, priors):
+        self.h = input_img_size[0] // downsample_factor
+        self.w = input_img_size[1] // downsample_factor
+        self.downsample = downsample_factor
+        self.priors = priors
+
+
+class ModelBlueprint:
+    def __init__(self, det_layers, cls_cnt):
+        self.det_layers = det_layers
+        self.cls_cnt = cls_cnt
+
+
+class DetLayer(DetLayerBlueprint):
+    """One detection scale.  `bbox` (list of 3 per-prior arrays [..,g,g,D]), `raw_output` and `det` hold the values of
+    the most recent run (None before the first run) - in the reference they are graph tensors."""
+
+    def __init__(self, input_img_size, downsample_factor, priors, layer_id):
+        super().__init__(input_img_size, downsample_factor, priors)
+        self.layer_id = layer_id
+        self.loc_loss = self.obj_loss = self.cls_loss = None
+        self.bbox = self.raw_output = self.det = None
+
+    def matches_blueprint(self, bp):
+        return (self.h, self.w, self.downsample, len(self.priors)) == (bp.h, bp.w, bp.downsample, len(bp.priors)) and all(
+            p.h == q.h and p.w == q.w for p, q in zip(self.priors, bp.priors))
+
+
+class Model:
+    """What `yolo.init_model(...).get_model()` returns: detection layers + column indices + an executor."""
+
+    def __init__(self, variant, engine_factory, inputs, img_size, priors, cls_cnt, obj_idx, cls_start_idx, T):
+        self.variant, self.inputs, self.cls_cnt = variant, inputs, cls_cnt
+        self.obj_idx, self.cls_start_idx, self.T = obj_idx, cls_start_idx, T
+        self.img_size = img_size
+        self.det_layers = [DetLayer(img_size, s, priors[s], i) for i, s in enumerate((32, 16, 8))]
+        self.layers = []                      # ModelBuilder's tensor list has no counterpart; see Engine.activation()
+        self.dn_out = self.det_net_1_out = self.det_net_2_out = self.det_net_3_out = None
+        self._engine_factory, self._engine, self._max_batch = engine_factory, None, 0
+
+    def matches_blueprint(self, blueprint):
+        return self.cls_cnt == blueprint.cls_cnt and all(
+            dl.matches_blueprint(bp) for dl, bp in zip(self.det_layers, blueprint.det_layers))
+
+    def engine(self, batch):
+        if self._engine is None or batch > self._max_batch:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine, self._max_batch = self._engine_factory(batch), batch
+        return self._engine
+
+    def execute(self, img, seed=0, image_index0=0, max_out=1000):
+        """One pass of the hot path for a host batch [B,H,W,3]: returns dict(rows, boxes, count, idx) of numpy arrays
+        and refreshes det_layers[*].bbox like a fetch of those tensors would."""
+        import torch
+        img = np.ascontiguousarray(img, np.float32)
+        assert img.ndim == 4 and tuple(img.shape[1:]) == tuple(self.img_size), (img.shape, self.img_size)
+        if self.variant == 'epistemic':
+            assert img.shape[0] == 1, 'the Bayesian model processes one image per run (inference_epistemic.py:193)'
+        eng = self.engine(img.shape[0])
+        boxes, cnt, idx, rows = eng.detect(torch.from_numpy(img).to(eng.device), seed=seed, image_index0=image_index0,
+                                           max_out=max_out, want_rows=True)
+        torch.cuda.synchronize(eng.device)
+        res = dict(rows=rows.cpu().numpy(), boxes=boxes.cpu().numpy(), count=cnt.cpu().numpy(), idx=idx.cpu().numpy())
+        off = 0
+        for dl in self.det_layers:                              # per-prior views in the reference's shapes
+            n = dl.h * dl.w
+            per = [res['rows'][:, off + p * n: off + (p + 1) * n].reshape(-1, dl.h, dl.w, res['rows'].shape[-1]) for p in range(3)]
+            dl.bbox = [p[0] for p in per] if self.variant == 'epistemic' else per
+            off += 3 * n
+        return res

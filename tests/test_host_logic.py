@@ -1,0 +1,187 @@
+"""CPU tests (no GPU): C-ABI surface, weight formats, reference-surface shims, ECP records, sharding + gather (gloo)."""
+import ctypes
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from byolo import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'byolo.h')).read()
+    declared = set(re.findall(r'\b(byolo_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.lib().byolo_version() == 1
+
+
+def test_no_cpu_fallback_and_argument_errors():
+    from byolo import _lib
+    lib = _lib.lib()
+    h = ctypes.c_void_p()
+    cfg = _lib.Config(variant=2, height=100, width=160, cls_cnt=2, max_batch=1, T=4, precision=2, drop_prob=0.1)
+    assert lib.byolo_create(ctypes.byref(cfg), ctypes.byref(h)) == -1          # 100 % 32 != 0 (yolov3.py:207-211)
+    assert b'multiple of 32' in lib.byolo_last_error()
+    if not torch.cuda.is_available():
+        cfg.height = 96
+        assert lib.byolo_create(ctypes.byref(cfg), ctypes.byref(h)) == -2
+        assert b'no CPU fallback' in lib.byolo_last_error()
+        import byolo
+        with pytest.raises(RuntimeError):
+            byolo.Engine('standard', (96, 160))
+
+
+def test_weight_blob_and_darknet_roundtrip(tmp_path):
+    from byolo import weights as W
+    for variant in W.VARIANTS:
+        table = W.layer_table(variant)
+        assert len(table) == 75 and table[-1][3] == W.det_channels(variant, 2)
+        assert sum(t[5] for t in table) == (15 if variant == 'epistemic' else 0)      # dropout-bearing convs
+    w = W.synthetic('aleatoric', 2, 3)
+    back = W.unpack(W.pack('aleatoric', w))
+    for a, b in zip(w, back):
+        assert a.keys() == b.keys() and all(np.array_equal(a[k], b[k]) for k in a)
+    n_params = sum(v.size for l in w for v in l.values())
+    assert abs(n_params - 61.6e6) < 0.3e6                                           # 61.5 M parameters
+    # darknet53.conv.74-style file: backbone only, consumed exactly (darknet.py:66)
+    table = W.layer_table('aleatoric')
+    path = str(tmp_path / 'dn.conv.74')
+    W.write_darknet(path, w[:52], table[:52])
+    got = W.read_darknet(path, table[:52])
+    assert len(got) == 52 and all(np.array_equal(got[i]['kernel'], w[i]['kernel']) for i in range(52))
+    with open(path, 'ab') as f:
+        f.write(b'\0\0\0\0')
+    with pytest.raises(AssertionError):
+        W.read_darknet(path, table[:52])
+
+
+def _cfg(**kw):
+    from lib_yolo import yolov3
+    c = {'full_img_size': [96, 160, 3], 'crop': False, 'cls_cnt': 2, 'priors': yolov3.ECP_9_PRIORS, 'aleatoric_loss': False,
+         'inference_mode': True, 'T': 4, 'weights': 'synthetic:1', 'implicit_background_class': True}
+    c.update(kw)
+    return c
+
+
+def test_model_classes_keep_the_reference_surface():
+    from byolo import compat
+    from lib_yolo import yolov3
+    for cls, oi, ci in ((yolov3.yolov3, 4, 5), (yolov3.yolov3_aleatoric, 9, 11), (yolov3.bayesian_yolov3_aleatoric, 14, 17)):
+        y = cls(_cfg())
+        assert (y.obj_idx, y.cls_start_idx, y.cls_cnt) == (oi, ci, 2) and list(y.img_size) == [96, 160, 3]
+        with pytest.raises(AssertionError):
+            y.get_model()
+        m = y.init_model(inputs=compat.Placeholder((1, 96, 160, 3)), training=False).get_model()
+        assert [(d.h, d.w, d.downsample) for d in m.det_layers] == [(3, 5, 32), (6, 10, 16), (12, 20, 8)]
+        assert m.matches_blueprint(y.blueprint) and (m.obj_idx, m.cls_start_idx) == (oi, ci)
+        with pytest.raises(Exception, match='only be initialized once'):
+            y.init_model(inputs=compat.Placeholder((1, 96, 160, 3)), training=False)
+    with pytest.raises(AssertionError):
+        yolov3.yolov3(_cfg(full_img_size=[100, 160, 3]))
+    with pytest.raises(KeyError):
+        yolov3.bayesian_yolov3_aleatoric({k: v for k, v in _cfg().items() if k != 'inference_mode'})
+    with pytest.raises(KeyError):
+        yolov3.bayesian_yolov3_aleatoric({k: v for k, v in _cfg().items() if k != 'T'})
+    # crop rescales priors without touching the shared table (the reference mutates it, model.py:11-15)
+    before = yolov3.ECP_9_PRIORS[32][0].h
+    y = yolov3.yolov3(_cfg(crop=True, crop_img_size=[64, 96, 3], full_img_size=[128, 192, 3]))
+    assert yolov3.ECP_9_PRIORS[32][0].h == before and abs(y.blueprint.det_layers[0].priors[0].h - before * 2) < 1e-12
+
+
+def test_ecp_records_and_script_surface(tmp_path):
+    import detect
+    import inference_aleatoric
+    import inference_epistemic
+    import inference_standard_yolov3
+    from byolo import compat, ecp
+    from lib_yolo import yolov3
+    for mod in (inference_standard_yolov3, inference_aleatoric, inference_epistemic):
+        for name in ('Inference', 'concat_bbox', 'nms', 'bbox_to_ecp_format', 'inference', 'main'):
+            assert hasattr(mod, name)
+    for name in ('box_op_standard', 'box_op_aleatoric', 'box_op_bayes', 'filter_boxes', 'preproces_boxes', 'draw_boxes',
+                 'load_img', 'load_model', 'do_it', 'main'):
+        assert hasattr(detect, name)
+    y = yolov3.bayesian_yolov3_aleatoric(_cfg())
+    m = y.init_model(inputs=compat.Placeholder((1, 96, 160, 3)), training=False).get_model()
+    row = np.arange(23, dtype=np.float32) / 23
+    rec = inference_epistemic.bbox_to_ecp_format(row, [96, 160, 3], m, _cfg())
+    assert rec['y0'] == float(row[0] * 96) and rec['x1'] == float(row[3] * 160)
+    assert rec['score'] == float(row[14]) * float(row[18]) and rec['identity'] == 'rider'
+    assert rec['obj_mutual_info'] == float(row[15]) and rec['cls_entropy'] == float(row[20]) and rec['prior_id'] == float(row[22])
+    ya = yolov3.yolov3_aleatoric(_cfg())
+    ma = ya.init_model(inputs=compat.Placeholder((1, 96, 160, 3)), training=False).get_model()
+    ra = inference_aleatoric.bbox_to_ecp_format(row[:16], [96, 160, 3], ma, _cfg())
+    assert ra['cls_entropy'] == ra['layer_id'] == ra['prior_id'] == float(row[13])     # reference quirk kept (:174-176)
+    out = ecp.write_ecp_json('epistemic', str(tmp_path), np.stack([row, row]), 'a/b/img_7.png', [96, 160, 3], m, _cfg())
+    assert os.path.basename(out) == 'img_7.json' and len(json.load(open(out))['children']) == 2
+    # filter / preprocess helpers of detect.py
+    boxes = np.stack([row, row * 0.1])
+    kept = detect.filter_boxes(boxes, 14, 0.1)
+    assert len(kept) == 1
+    pp = detect.preproces_boxes([96, 160, 3], kept, 14, 17, 2, _cfg(), {1: 'ped', 2: 'rider'})
+    assert pp[0]['cls'] == 'rider' and 0 <= pp[0]['y0'] <= 96
+    # weight lookup by step, like the checkpoint lookup of the reference
+    os.makedirs(tmp_path / 'ck' / 'run')
+    for s in (10, 200):
+        open(tmp_path / 'ck' / 'run' / ('weights-%d.byw' % s), 'wb').close()
+    c = {'checkpoint_path': str(tmp_path / 'ck'), 'run_id': 'run', 'step': 'last'}
+    assert ecp.find_weights(c)[1] == '200' and ecp.find_weights(dict(c, step=10))[1] == '10'
+
+
+def test_image_dataset_iterates_once(tmp_path):
+    from byolo import compat
+    rng = np.random.default_rng(0)
+    for i in range(3):
+        np.save(tmp_path / ('im%d.npy' % i), rng.random((96, 160, 3), dtype=np.float32))
+    ds = compat.ImageDataset({'data': {'file_pattern': str(tmp_path / '*.npy')}, 'batch_size': 2, 'full_img_size': [96, 160, 3]})
+    src, names = ds.iterator.get_next()
+    a = src.next_batch()
+    assert a.shape == (2, 96, 160, 3) and src.last_files[0][0].decode().endswith('im0.npy')
+    assert src.next_batch().shape[0] == 1
+    with pytest.raises(compat.OutOfRangeError):
+        src.next_batch()
+
+
+def _gloo_worker(rank, world, port, n_images, ret):
+    import torch.distributed as dist
+    sys.path[:0] = [os.path.join(ROOT, 'bayesian-yolov3_b200')]
+    from byolo import dist as bd
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+
+    def run_local(imgs, index0):                     # stub hot path: result depends only on the GLOBAL image index
+        b = imgs.shape[0]
+        boxes = torch.zeros((b, 5, 3))
+        cnt = torch.zeros((b,), dtype=torch.int32)
+        for i in range(b):
+            g = index0 + i
+            cnt[i] = g % 5 + 1
+            boxes[i, :cnt[i]] = float(g) + imgs[i].sum()
+        return boxes, cnt
+
+    imgs = torch.arange(n_images, dtype=torch.float32).view(n_images, 1, 1, 1).expand(n_images, 2, 2, 3).contiguous()
+    boxes, cnt = bd.ShardedDetector(run_local).detect(imgs)
+    single_b, single_c = run_local(imgs, 0)
+    ok = torch.equal(boxes, single_b) and torch.equal(cnt, single_c)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_images', [4, 5])
+def test_sharded_detect_equals_single_rank_gloo(n_images):
+    import torch.multiprocessing as mp
+    from byolo import dist as bd
+    assert [bd.shard_range(5, r, 2) for r in range(2)] == [(0, 3), (3, 5)]
+    assert [bd.shard_range(32, r, 8) for r in range(8)][-1] == (28, 32)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 2000 + n_images
+    mp.spawn(_gloo_worker, args=(2, port, n_images, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]

@@ -37,12 +37,13 @@ def filter_boxes(boxes, obj_idx, thresh):
 def preproces_boxes(img_size, boxes, obj_idx, cls_start_idx, cls_cnt, config, cls_mapping=None):
     out = []
     for box in boxes:
-        cls_idx = np.argmax(box[cls_start_idx:cls_start_idx + cls_cnt])
-        if config['implicit_background_class']:
-            cls_idx += 1
+        cls_col = int(np.argmax(box[cls_start_idx:cls_start_idx + cls_cnt]))
+        cls_idx = cls_col + 1 if config['implicit_background_class'] else cls_col
         cls = cls_mapping[cls_idx] if cls_mapping else cls_idx
-        # as written in the reference (detect.py:51): indexed AFTER the +1 background shift
-        cls_score = box[cls_idx + cls_start_idx]
+        # FLAGGED deviation: the reference indexes the score AFTER the +1 background shift (detect.py:44-51), which
+        # reads the neighbouring column (or raises IndexError for the 7-column standard rows); the winning class's
+        # own score is used here.
+        cls_score = box[cls_col + cls_start_idx]
         y0, x0, y1, x1 = (np.clip(box[i], 0, 1) * img_size[i % 2] for i in range(4))
         out.append({'cls': cls, 'score': box[obj_idx] * cls_score, 'obj_score': box[obj_idx], 'cls_score': cls_score,
                     'y0': y0, 'x0': x0, 'y1': y1, 'x1': x1})

@@ -32,6 +32,8 @@ SIGNATURES = {
     'byolo_nms': (C.c_int, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P]),
     'byolo_detect': (C.c_int, [_P, _P, _I, _U64, _I, _F, _I, _P, _P, _P, _P, _P]),
     'byolo_detect_host': (C.c_int, [_P, _P, _I, _U64, _I, _F, _I, _P, _P, _P]),
+    'byolo_submit_host': (C.c_int, [_P, _P, _I, _U64, _I, _F, _I, _P, _P, _I, _P]),
+    'byolo_wait_host': (C.c_int, [_P, _I]),
     'byolo_decode': (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
     'byolo_conv_layer': (C.c_int, [_I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _U64, _I, _F,
                                    _P, _P]),

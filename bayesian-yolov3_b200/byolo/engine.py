@@ -101,6 +101,20 @@ class Engine:
                                               _np_ptr(out[0]), _np_ptr(out[1]), _stream()))
         return out
 
+    def submit_host(self, img_host, out, slot, seed=0, image_index0=0, max_out=1000, iou_thr=0.5):
+        """Pipelined detect_host: enqueue H2D -> detect -> D2H for `slot` (0|1); `out` = (rows [B,max_out,D], count [B])
+        host arrays (pinned for real overlap) that wait_host(slot) guarantees to be filled."""
+        a = img_host.numpy() if isinstance(img_host, torch.Tensor) else img_host
+        assert a.dtype == np.float32 and a.shape[1:] == (self.H, self.W, 3) and a.flags['C_CONTIGUOUS']
+        o0 = out[0].numpy() if isinstance(out[0], torch.Tensor) else out[0]
+        o1 = out[1].numpy() if isinstance(out[1], torch.Tensor) else out[1]
+        assert o0.dtype == np.float32 and o1.dtype == np.int32
+        _lib.check(self.lib.byolo_submit_host(self.h, _np_ptr(a), a.shape[0], seed, image_index0, iou_thr, max_out,
+                                              _np_ptr(o0), _np_ptr(o1), slot, _stream()))
+
+    def wait_host(self, slot):
+        _lib.check(self.lib.byolo_wait_host(self.h, slot))
+
     def decode(self, raws, B):
         """raws: three dense fp32 cuda tensors [B*T,g,g,ch] -> rows [B,N,D]."""
         rows = torch.empty((B, self.N, self.D), dtype=torch.float32, device=raws[0].device)

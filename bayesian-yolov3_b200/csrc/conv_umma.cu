@@ -182,6 +182,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias
+    // staging - none of it produced by the previous kernel) may overlap the tail of the previous grid; from here on we
+    // read its output.  The next grid may start its own prologue as soon as our CTAs retire.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -550,8 +555,17 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
 }
 
 int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
-    conv_umma_kernel<<<L.grid, kThreads, L.smem_bytes, st>>>(L.a1, L.a2, L.b, L.o, L.p);
-    BY_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(L.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel, L.a1, L.a2, L.b, L.o, L.p));
     return 0;
 }
 

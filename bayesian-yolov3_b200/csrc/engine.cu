@@ -147,6 +147,14 @@ struct byolo_engine {
     std::map<int, std::unique_ptr<Plan>> plans;
     Plan* last_plan = nullptr;     // plan of the most recent forward (byolo_get_activation)
     bool profiling = false;
+    // pipelined host entry (byolo_submit_host / byolo_wait_host): two slots, separate H2D and D2H copy streams
+    struct HostSlot {
+        float* img = nullptr; float* out = nullptr; int* cnt = nullptr;
+        size_t img_bytes = 0, out_bytes = 0;
+        cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
+        bool used = false;
+    } slot[2];
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     int N = 0, D = 0, obj_idx = 0, cls_start = 0;
     int gh[3], gw[3];
     bool act_half() const { return cfg.precision != BYOLO_PREC_FP32; }
@@ -156,6 +164,14 @@ struct byolo_engine {
     ~byolo_engine() {
         plans.clear();
         for (auto& w : weights) w.release();
+        for (auto& s : slot) {
+            cudaFree(s.img); cudaFree(s.out); cudaFree(s.cnt);
+            if (s.h2d) cudaEventDestroy(s.h2d);
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.d2h) cudaEventDestroy(s.d2h);
+        }
+        if (s_h2d) cudaStreamDestroy(s_h2d);
+        if (s_d2h) cudaStreamDestroy(s_d2h);
     }
 };
 
@@ -532,6 +548,60 @@ int byolo_detect_host(byolo_handle h, const float* img_host, int32_t B, uint64_t
     BY_CUDA(cudaMemcpyAsync(out_rows_host, pl->out_stage, sizeof(float) * (size_t)B * max_out * h->D, cudaMemcpyDeviceToHost, st));
     BY_CUDA(cudaMemcpyAsync(out_count_host, pl->cnt_stage, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     BY_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int byolo_submit_host(byolo_handle h, const float* img_host, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
+                      int32_t max_out, float* out_rows_host, int32_t* out_count_host, int32_t slot, void* stream) {
+    BY_REQUIRE(h && img_host && out_rows_host && out_count_host, "null argument");
+    BY_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->s_h2d) {
+        BY_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        BY_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    }
+    byolo_engine::HostSlot& s = h->slot[slot];
+    if (!s.h2d) {
+        BY_CUDA(cudaEventCreateWithFlags(&s.h2d, cudaEventDisableTiming));
+        BY_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        BY_CUDA(cudaEventCreateWithFlags(&s.d2h, cudaEventDisableTiming));
+    }
+    const size_t img_bytes = sizeof(float) * (size_t)B * h->cfg.height * h->cfg.width * 3;
+    const size_t out_bytes = sizeof(float) * (size_t)B * max_out * h->D;
+    if (s.img_bytes < img_bytes) {
+        BY_CUDA(cudaDeviceSynchronize());
+        cudaFree(s.img); s.img = nullptr;
+        BY_CUDA(cudaMalloc(&s.img, img_bytes));
+        s.img_bytes = img_bytes;
+    }
+    if (s.out_bytes < out_bytes) {
+        BY_CUDA(cudaDeviceSynchronize());
+        cudaFree(s.out); cudaFree(s.cnt); s.out = nullptr; s.cnt = nullptr;
+        BY_CUDA(cudaMalloc(&s.out, out_bytes));
+        BY_CUDA(cudaMalloc(&s.cnt, sizeof(int) * h->cfg.max_batch));
+        s.out_bytes = out_bytes;
+    }
+    // H2D of this step may run while the previous step computes; it only has to wait for the last compute that READ
+    // this slot's staging buffer
+    if (s.used) BY_CUDA(cudaStreamWaitEvent(h->s_h2d, s.done, 0));
+    BY_CUDA(cudaMemcpyAsync(s.img, img_host, img_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    BY_CUDA(cudaEventRecord(s.h2d, h->s_h2d));
+    BY_CUDA(cudaStreamWaitEvent(st, s.h2d, 0));
+    if (s.used) BY_CUDA(cudaStreamWaitEvent(st, s.d2h, 0));          // previous results of this slot have left the device
+    if (int r = byolo_detect(h, s.img, B, seed, image_index0, iou_thr, max_out, nullptr, s.out, nullptr, s.cnt, stream)) return r;
+    BY_CUDA(cudaEventRecord(s.done, st));
+    BY_CUDA(cudaStreamWaitEvent(h->s_d2h, s.done, 0));
+    BY_CUDA(cudaMemcpyAsync(out_rows_host, s.out, out_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+    BY_CUDA(cudaMemcpyAsync(out_count_host, s.cnt, sizeof(int) * B, cudaMemcpyDeviceToHost, h->s_d2h));
+    BY_CUDA(cudaEventRecord(s.d2h, h->s_d2h));
+    s.used = true;
+    return 0;
+}
+
+int byolo_wait_host(byolo_handle h, int32_t slot) {
+    BY_REQUIRE(h && (slot == 0 || slot == 1), "bad argument");
+    BY_REQUIRE(h->slot[slot].used, "nothing was submitted on this slot");
+    BY_CUDA(cudaEventSynchronize(h->slot[slot].d2h));
     return 0;
 }
 

@@ -84,6 +84,14 @@ int byolo_detect(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed,
 int byolo_detect_host(byolo_handle h, const float* img_host, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
                       int32_t max_out, float* out_rows_host, int32_t* out_count_host, void* stream);
 
+/* Pipelined form of byolo_detect_host for streams of batches (the reference overlaps the JSON writer thread with the
+ * next sess.run, inference_epistemic.py:78-83; here the copies overlap too): submit enqueues H2D(images) -> detect ->
+ * D2H(results) for slot 0|1 and returns at once; wait blocks until that slot's results are in the host buffers passed
+ * to submit.  Alternate the slots: the H2D of batch i+1 then overlaps the compute of batch i.  Pinned host memory. */
+int byolo_submit_host(byolo_handle h, const float* img_host, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
+                      int32_t max_out, float* out_rows_host, int32_t* out_count_host, int32_t slot, void* stream);
+int byolo_wait_host(byolo_handle h, int32_t slot);
+
 /* Head decode alone on raw head outputs (layers.py:191-502 + concat): raw{0,1,2}_dev dense fp32 [B*T, g, g, ch],
  * stride 32/16/8.  Test hook and the `DetLayer.raw_output -> bbox` step of model.py:107-185. */
 int byolo_decode(byolo_handle h, const float* raw0_dev, const float* raw1_dev, const float* raw2_dev, int32_t B,

@@ -174,18 +174,40 @@ def main():
     prof = eng.profile_read()
     eng.profile(False)
 
-    # ---- end to end through the host-buffer entry point (H2D of every step's images, D2H of its detections) ----
-    out = (np.empty((B, 1000, eng.D), np.float32), np.empty((B,), np.int32))
+    # ---- end to end through the host-buffer entry points (H2D of every step's images, D2H of its detections) ----
+    # pipelined form: two slots, so the copy of batch i+1 overlaps the compute of batch i; every step still moves its own
+    # 71 MB in and 1.5 MB out inside the timed region and the last wait_host is inside it too.
+    outs = [(torch.empty((B, 1000, eng.D), dtype=torch.float32).pin_memory(), torch.empty((B,), dtype=torch.int32).pin_memory())
+            for _ in range(2)]
     for i in range(2):
-        eng.detect_host(host[i % n_rot], seed=1003, image_index0=rank * B, out=out)
+        eng.submit_host(host[i % n_rot], outs[i % 2], i % 2, seed=1003, image_index0=rank * B)
+    eng.wait_host(0)
+    eng.wait_host(1)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     e0.record()
     for i in range(K):
-        eng.detect_host(host[i % n_rot], seed=1003, image_index0=rank * B, out=out)
+        if i >= 2:
+            eng.wait_host(i % 2)
+        eng.submit_host(host[i % n_rot], outs[i % 2], i % 2, seed=1003, image_index0=rank * B)
+    for i in range(max(K - 2, 0), K):
+        eng.wait_host(i % 2)
     e1.record()
     barrier()
+    ms_e2e_wall = (time.perf_counter() - t_host0) * 1e3     # barrier() above synchronised: wall time covers the last D2H
     ms_e2e = e0.elapsed_time(e1)
+    # serial form (one call = copy in, compute, copy out, sync), for reference
+    out = (np.empty((B, 1000, eng.D), np.float32), np.empty((B,), np.int32))
+    eng.detect_host(host[0], seed=1003, image_index0=rank * B, out=out)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(min(K, 5)):
+        eng.detect_host(host[i % n_rot], seed=1003, image_index0=rank * B, out=out)
+    s1.record()
+    barrier()
+    ms_serial = s0.elapsed_time(s1) / min(K, 5)
     clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev)
@@ -206,8 +228,10 @@ def main():
                               l2='4 rotating input batches (284 MB) > L2; per-step activations (GBs) stream through HBM'),
                'p50_ms_per_img': ms / K / B,
                'clocks': clocks,
-               'e2e': {'value': world * B * K / (ms_e2e * 1e-3), 'unit': 'images/s',
-                       'h2d_bytes_per_step': B * S * S * 3 * 4, 'd2h_bytes_per_step': B * 1000 * eng.D * 4 + B * 4},
+               'e2e': {'value': world * B * K / (max(ms_e2e, ms_e2e_wall) * 1e-3), 'unit': 'images/s',
+                       'h2d_bytes_per_step': B * S * S * 3 * 4, 'd2h_bytes_per_step': B * 1000 * eng.D * 4 + B * 4,
+                       'api': 'byolo_submit_host/byolo_wait_host, 2 slots, pinned host buffers',
+                       'serial_detect_host_ms_per_step': ms_serial},
                'gpu_launches': eng.launch_count(B) * K,
                'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (all %d conv launches of a step)' % len(conv),
                             'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,

@@ -141,9 +141,11 @@ class Engine:
         """Per-launch records of the last profiled detect(): list of dict(ms, kind, layer, flops)."""
         cap = 256
         ms, kind, layer, fl = np.zeros(cap, np.float32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float64)
-        n = _lib.check(self.lib.byolo_profile_read(self.h, _np_ptr(ms), _np_ptr(kind), _np_ptr(layer), _np_ptr(fl), cap))
+        mhz = np.zeros(cap, np.float32)
+        n = _lib.check(self.lib.byolo_profile_read(self.h, _np_ptr(ms), _np_ptr(kind), _np_ptr(layer), _np_ptr(fl), _np_ptr(mhz), cap))
         names = ('stem', 'conv', 'stack', 'decode', 'nms')
-        return [dict(ms=float(ms[i]), kind=names[kind[i]], layer=int(layer[i]), flops=float(fl[i])) for i in range(n)]
+        return [dict(ms=float(ms[i]), kind=names[kind[i]], layer=int(layer[i]), flops=float(fl[i]), sm_mhz=float(mhz[i]))
+                for i in range(n)]
 
     def launch_count(self, B):
         return _lib.check(self.lib.byolo_launch_count(self.h, B))

@@ -15,6 +15,7 @@
 // allocator, warps 4-11 epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant split the columns); smem ring of `num_stages` {A,B} tiles with
 // full/empty mbarriers; two TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -61,6 +62,49 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
         "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+// ---- 2-CTA (cta_group::2) forms: the TMA of either CTA signals the LEADER's barrier (peer bit 24 cleared), the
+// leader's MMA commits are multicast to the barrier at the same offset in both CTAs.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"((uint64_t)map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {     // arrive on CTA `cta`'s copy of `bar`
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src),
@@ -139,6 +183,10 @@ struct SmemCtl {
     float bias[kMaxBias];
 };
 
+// CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2) works on 256 rows x BN: each CTA stages its own
+// 128 A rows and HALF of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) for both, every CTA runs
+// the epilogue of its own 128 accumulator rows.  Per SM and MMA cycle this moves 2/3 of the bytes of CG = 1.
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o, const UmmaParams p) {
@@ -153,6 +201,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_kb = p.taps * (p.kb1 + p.kb2);
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
+    const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a1);
@@ -167,19 +217,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&ctl->acc_full[s]), 1);
-            mbar_init(smem_u32(&ctl->acc_empty[s]), kEpiWarps);
+            mbar_init(smem_u32(&ctl->acc_empty[s]), kEpiWarps * CG);      // CG = 2: both CTAs' epilogues release the leader
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
-                     "r"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
+                         "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
+                         "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     for (int i = threadIdx.x; i < p.num_n_tiles * p.BN; i += kThreads) ctl->bias[i] = __ldg(p.ep.bias + i);
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();           // the peer's barriers exist before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias
@@ -187,14 +245,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     // read its output.  The next grid may start its own prologue as soon as our CTAs retire.
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (p.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        p.clk[0] = clock64();
+        p.clk[1] = g;
+    }
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.num_n_tiles;
-                const int n0 = (tile % p.num_n_tiles) * p.BN;
+            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+                const int m_tile = (tile / p.num_n_tiles) * CG + (int)rank;
+                const int n0 = (tile % p.num_n_tiles) * p.BN + (int)rank * p.b_rows * (CG - 1);   // CG = 2: my half of B
                 int m0 = m_tile * kTileM, tx = 0, ty = 0, bi = 0;
                 if (p.s2) {
                     tx = m_tile % p.tiles_x;
@@ -207,8 +271,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                     mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1);
                     const uint32_t full = smem_u32(&ctl->full[stage]);
                     const uint32_t sa = ring + stage * stage_bytes, sb = sa + p.a_bytes;
-                    mbar_expect_tx(full, stage_bytes);
+                    if (rank == 0) mbar_expect_tx(full, stage_bytes * CG);     // bytes of both CTAs land on the leader's barrier
                     const int r = tap / 3, s = tap - 3 * r;
+                    if constexpr (CG == 2) {
+                        const int shift = (p.taps == 9) ? (r - 1) * p.in_PW + (s - 1) : 0;
+                        if (cb < p.kb1) tma_load_2d_2cta(sa, &map_a1, full, cb * p.BK, m0 + shift);
+                        else tma_load_2d_2cta(sa, &map_a2, full, (cb - p.kb1) * p.BK, m0);
+                        tma_load_2d_2cta(sb, &map_b, full, kb * p.BK, n0);
+                        if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
+                        continue;
+                    }
                     if (p.s2) {
                         tma_load_4d(sa, &map_a1, full, cb * p.BK, 2 * tx * p.BW + s, 2 * ty * p.BH + r, bi * p.BI);
                     } else if (cb < p.kb1) {
@@ -223,11 +295,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
+        // ================================ MMA issuer (leader CTA only when CG = 2) ================================
+        if (lane == 0 && rank == 0) {
             uint32_t it = 0, tile_it = 0;
             const int mma_per_kb = p.BK / 16;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
+            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++tile_it) {
                 const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
                 mbar_wait(smem_u32(&ctl->acc_empty[as]), aphase ^ 1);
                 tc_fence_after();
@@ -241,11 +313,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                     const uint64_t bdesc = make_smem_desc(sb, p.sbo_bytes, p.layout_type);
                     for (int k = 0; k < mma_per_kb; ++k) {
                         // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
+                        if constexpr (CG == 1) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
+                        else umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
                     }
-                    umma_commit(smem_u32(&ctl->empty[stage]));       // frees the smem slot once these MMAs retire
+                    // frees the smem slot (in both CTAs when CG = 2) once these MMAs retire
+                    if constexpr (CG == 1) umma_commit(smem_u32(&ctl->empty[stage]));
+                    else umma_commit_2cta(smem_u32(&ctl->empty[stage]));
                 }
-                umma_commit(smem_u32(&ctl->acc_full[as]));           // accumulator complete -> epilogue
+                // accumulator complete -> epilogue(s)
+                if constexpr (CG == 1) umma_commit(smem_u32(&ctl->acc_full[as]));
+                else umma_commit_2cta(smem_u32(&ctl->acc_full[as]));
             }
         }
     } else if (warp >= 4) {
@@ -271,9 +348,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         const uint32_t stg_row = stg + lane * 64;
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
         uint32_t tile_it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
+        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++tile_it) {
             const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
-            const int m_tile = tile / p.num_n_tiles;
+            const int m_tile = (tile / p.num_n_tiles) * CG + (int)rank;
             const int n0 = (tile % p.num_n_tiles) * p.BN;
             const int i = quad * 32 + lane;              // row of the tile == TMEM lane
             int s, y, x;
@@ -400,7 +477,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty[as]));
+            if (lane == 0) {
+                if constexpr (CG == 1) mbar_arrive(smem_u32(&ctl->acc_empty[as]));
+                else mbar_arrive_cluster(smem_u32(&ctl->acc_empty[as]), 0);      // the leader's MMA thread waits for both CTAs
+            }
         }
         if (tma_out && lane == 0) bulk_wait0();          // all output writes complete before the CTA retires
     }
@@ -408,8 +488,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     // ---------------- teardown ----------------
     tc_fence_before();
     __syncthreads();
+    if (p.clk && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        p.clk[2] = clock64();
+        p.clk[3] = g;
+    }
+    if constexpr (CG == 2) cluster_sync_all();           // the peer may not retire while the leader's MMAs read its smem
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if constexpr (CG == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -480,6 +570,10 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.BN = std::min(q.cout_pad, 256);
     BY_REQUIRE(q.cout_pad % p.BN == 0, "cout_pad must be a multiple of the N tile");
     p.num_n_tiles = q.cout_pad / p.BN;
+    // CTA pairs for the feed-bound shapes: 3x3 stride-1 convs with wide N tiles
+    static const int cg_env = getenv("BYOLO_CG") ? atoi(getenv("BYOLO_CG")) : 0;     // 1 = force off, 2 = default policy
+    p.cg = (cg_env != 1 && q.k == 3 && q.stride == 1 && p.BN >= 128 && p.BK == 64) ? 2 : 1;
+    p.b_rows = p.BN / p.cg;
     p.in_PW = g.PW();
     p.s2 = q.stride == 2;
     p.gout.S = g.S;
@@ -493,9 +587,9 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.sbo_bytes = 8 * swz;
     p.layout_type = (swz == 128) ? 2u : 4u;                       // SWIZZLE_128B / SWIZZLE_64B
     p.a_bytes = kTileM * swz;
-    p.b_bytes = p.BN * swz;
-    // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-    p.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    p.b_bytes = p.b_rows * swz;
+    // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for a CTA pair)
+    p.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((kTileM * p.cg) >> 4) << 24);
     const int budget = 227 * 1024 - 1024 - (int)sizeof(SmemCtl) - kEpiWarps * kStageOutBytes - 64;
     p.num_stages = std::max(2, std::min(kMaxStages, budget / (p.a_bytes + p.b_bytes)));
     L->smem_bytes = p.num_stages * (p.a_bytes + p.b_bytes) + 1024 + sizeof(SmemCtl) + kEpiWarps * kStageOutBytes + 64;
@@ -528,7 +622,7 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     {
         const uint64_t K = (uint64_t)p.taps * (C1 + C2);
         uint64_t d[2] = {K, (uint64_t)q.cout_pad}, s[1] = {K * 2};
-        uint32_t box[2] = {(uint32_t)p.BK, (uint32_t)p.BN};
+        uint32_t box[2] = {(uint32_t)p.BK, (uint32_t)p.b_rows};
         if (int e = make_map(&L->b, q.w16, 2, d, s, box, one, swz)) return e;
     }
     L->o = L->b;
@@ -540,15 +634,17 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
         uint32_t box[2] = {(uint32_t)(f32 ? 16 : 32), 32u};
         if (int e = make_map(&L->o, q.ep.out, 2, d, st, box, one, 64, f32)) return e;
     }
-    p.num_tiles = p.num_m_tiles * p.num_n_tiles;
+    p.num_tiles = ((p.num_m_tiles + p.cg - 1) / p.cg) * p.num_n_tiles;      // CG = 2: tiles are pairs of M tiles
     int dev = 0, sms = 0;
     BY_CUDA(cudaGetDevice(&dev));
     BY_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    L->grid = std::min(p.num_tiles, sms);
+    L->grid = std::min(p.num_tiles * p.cg, sms / p.cg * p.cg);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     BY_CUDA(attr_err);
     return 0;
@@ -560,12 +656,21 @@ int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = L.smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel, L.a1, L.a2, L.b, L.o, L.p));
+    if (L.p.cg == 2) {
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2>, L.a1, L.a2, L.b, L.o, L.p));
+    } else {
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1>, L.a1, L.a2, L.b, L.o, L.p));
+    }
     return 0;
 }
 

@@ -7,6 +7,8 @@ namespace byolo {
 struct UmmaParams {
     int num_m_tiles, num_n_tiles, num_tiles;
     int BN, BK, num_stages;
+    int cg;                        // CTAs per tile: 1, or 2 (cta_group::2 pair, M = 256)
+    int b_rows;                    // rows of B each CTA stages (BN / cg)
     int a_bytes, b_bytes;          // bytes of one A / B stage tile
     int taps;                      // 1 | 9
     int kb1, kb2;                  // K blocks per tap read from in1 / in2
@@ -17,6 +19,7 @@ struct UmmaParams {
     Epilogue ep;
     uint32_t idesc;                // tcgen05 instruction descriptor
     uint32_t sbo_bytes, layout_type;
+    unsigned long long* clk;       // profiling: {clock64, globaltimer} at start and end of CTA 0 (effective SM clock), or null
 };
 
 struct UmmaLaunch {

@@ -126,10 +126,12 @@ struct Plan {
     float* out_stage = nullptr;
     int* cnt_stage = nullptr;
     int stage_max_out = 0;
+    unsigned long long* clk = nullptr;   // profiling: 4 x u64 per step (conv kernels write SM clock / global timer pairs)
     std::vector<cudaEvent_t> ev;    // profiling: steps.size() + 3 events (one before each launch, decode, nms, end)
     bool ev_recorded = false;
     ~Plan() {
         for (auto& x : ev) cudaEventDestroy(x);
+        cudaFree(clk);
         for (auto& b : bufs) cudaFree(b.ptr);
         cudaFree(rows_scratch); cudaFree(img_stage); cudaFree(out_stage); cudaFree(cnt_stage);
     }
@@ -332,6 +334,8 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
     if (prof && pl->ev.empty()) {
         pl->ev.resize(pl->steps.size() + 3);
         for (auto& x : pl->ev) BY_CUDA(cudaEventCreate(&x));
+        BY_CUDA(cudaMalloc(&pl->clk, sizeof(unsigned long long) * 4 * pl->steps.size()));
+        BY_CUDA(cudaMemset(pl->clk, 0, sizeof(unsigned long long) * 4 * pl->steps.size()));
     }
     size_t ei = 0;
     for (Step& s : pl->steps) {
@@ -345,6 +349,7 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
             if (c.precision == BYOLO_PREC_FP16) {
                 Dropout& d = s.ul.p.ep.drop;
                 d.seed_lo = (uint32_t)seed; d.seed_hi = (uint32_t)(seed >> 32); d.image0 = image0;
+                s.ul.p.clk = prof ? pl->clk + 4 * (ei - 1) : nullptr;
                 if (int r = umma_launch(s.ul, st)) return r;
             } else {
                 Dropout& d = s.prob.ep.drop;
@@ -498,16 +503,21 @@ int byolo_profile(byolo_handle h, int32_t enable) {
     return 0;
 }
 
-int byolo_profile_read(byolo_handle h, float* ms, int32_t* kind, int32_t* layer, double* flops, int32_t capacity) {
-    BY_REQUIRE(h && ms && kind && layer && flops, "null argument");
+int byolo_profile_read(byolo_handle h, float* ms, int32_t* kind, int32_t* layer, double* flops, float* sm_mhz, int32_t capacity) {
+    BY_REQUIRE(h && ms && kind && layer && flops && sm_mhz, "null argument");
     Plan* pl = h->last_plan;
     BY_REQUIRE(pl && pl->ev_recorded, "no profiled byolo_detect has completed");
     const int n = (int)pl->steps.size() + 2;
     BY_REQUIRE(capacity >= n, "capacity too small");
     BY_CUDA(cudaEventSynchronize(pl->ev.back()));
+    std::vector<unsigned long long> clk(4 * pl->steps.size(), 0ull);
+    BY_CUDA(cudaMemcpy(clk.data(), pl->clk, sizeof(unsigned long long) * clk.size(), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) {
         BY_CUDA(cudaEventElapsedTime(&ms[i], pl->ev[i], pl->ev[i + 1]));
         flops[i] = 0.0;
+        sm_mhz[i] = 0.f;
+        if (i < (int)pl->steps.size() && clk[4 * i + 3] > clk[4 * i + 1])
+            sm_mhz[i] = (float)((double)(clk[4 * i + 2] - clk[4 * i]) * 1e3 / (double)(clk[4 * i + 3] - clk[4 * i + 1]));
         if (i < (int)pl->steps.size()) {
             const Step& s = pl->steps[i];
             kind[i] = (int)s.kind;

@@ -238,10 +238,13 @@ def main():
                             'peak_source': peak_src, 'traffic': None, 'conv_share_of_step': conv_ms / step_ms if step_ms else None,
                             'flops_per_image': eng.flops_per_image(), 'step_tflops': eng.flops_per_image() * B / (ms / K * 1e-3) / 1e12},
                'breakdown_ms': {k: sum(p['ms'] for p in prof if p['kind'] == k) for k in ('stem', 'conv', 'stack', 'decode', 'nms')}}
+        big = [p for p in conv if p['ms'] > 0.3 and p['sm_mhz'] > 0]
+        if big:      # effective SM clock inside the long conv launches (clock64/globaltimer): shows power-cap throttling
+            res['clocks']['sm_mhz_in_conv_kernels'] = sum(p['sm_mhz'] * p['ms'] for p in big) / sum(p['ms'] for p in big)
         if args.layers:
             for p in prof:
                 tf = p['flops'] / (p['ms'] * 1e-3) / 1e12 if p['ms'] > 0 else 0
-                print('%-6s layer %3d  %8.3f ms  %8.1f TFLOP/s' % (p['kind'], p['layer'], p['ms'], tf), file=sys.stderr)
+                print('%-6s layer %3d  %8.3f ms  %8.1f TFLOP/s  %6.0f MHz' % (p['kind'], p['layer'], p['ms'], tf, p['sm_mhz']), file=sys.stderr)
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = 8                                   # ~5 s of CPU work on 8 cores
             v, cores = cpu_oracle_rate(n_cpu, T, S)

@@ -193,7 +193,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     // ring of {A,B} tiles, 1024B aligned (SWIZZLE_128B atoms are 1024B); output staging and control block behind it
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    const uint32_t kb_bytes = p.a_bytes + p.b_bytes;              // one K block of {A, B}
+    const uint32_t stage_bytes = kb_bytes * p.kbs;                // a stage holds kbs K blocks (8 MMAs per commit when kbs = 2)
     const uint32_t out_stage = ring + p.num_stages * stage_bytes;
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (ring - smem_u32(smem_raw)) + (size_t)p.num_stages * stage_bytes +
                                               kEpiWarps * kStageOutBytes);
@@ -266,31 +267,40 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                     bi = m_tile / (p.tiles_x * p.tiles_y);
                 }
                 int tap = 0, cb = 0;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                for (int kb0 = 0; kb0 < num_kb; kb0 += p.kbs, ++it) {
+                    const int nkb = min(p.kbs, num_kb - kb0);
                     const uint32_t stage = it % p.num_stages, phase = (it / p.num_stages) & 1;
                     mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1);
                     const uint32_t full = smem_u32(&ctl->full[stage]);
-                    const uint32_t sa = ring + stage * stage_bytes, sb = sa + p.a_bytes;
-                    if (rank == 0) mbar_expect_tx(full, stage_bytes * CG);     // bytes of both CTAs land on the leader's barrier
-                    const int r = tap / 3, s = tap - 3 * r;
-                    if constexpr (CG == 2) {
-                        const int shift = (p.taps == 9) ? (r - 1) * p.in_PW + (s - 1) : 0;
-                        if (cb < p.kb1) tma_load_2d_2cta(sa, &map_a1, full, cb * p.BK, m0 + shift);
-                        else tma_load_2d_2cta(sa, &map_a2, full, (cb - p.kb1) * p.BK, m0);
-                        tma_load_2d_2cta(sb, &map_b, full, kb * p.BK, n0);
-                        if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
+                    if (p.dbg & 1) {                   // experiment: barrier traffic without any bytes moving
+                        if (rank == 0) mbar_arrive(full);
+                        for (int j = 0; j < nkb; ++j)
+                            if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
                         continue;
                     }
-                    if (p.s2) {
-                        tma_load_4d(sa, &map_a1, full, cb * p.BK, 2 * tx * p.BW + s, 2 * ty * p.BH + r, bi * p.BI);
-                    } else if (cb < p.kb1) {
-                        const int shift = (p.taps == 9) ? (r - 1) * p.in_PW + (s - 1) : 0;
-                        tma_load_2d(sa, &map_a1, full, cb * p.BK, m0 + shift);
-                    } else {
-                        tma_load_2d(sa, &map_a2, full, (cb - p.kb1) * p.BK, m0);
+                    if (rank == 0) mbar_expect_tx(full, kb_bytes * nkb * CG);   // bytes of both CTAs land on the leader's barrier
+                    for (int j = 0; j < nkb; ++j) {
+                        const int kb = kb0 + j;
+                        const uint32_t sa = ring + stage * stage_bytes + j * kb_bytes, sb = sa + p.a_bytes;
+                        const int r = tap / 3, s = tap - 3 * r;
+                        if constexpr (CG == 2) {
+                            const int shift = (p.taps == 9) ? (r - 1) * p.in_PW + (s - 1) : 0;
+                            if (cb < p.kb1) tma_load_2d_2cta(sa, &map_a1, full, cb * p.BK, m0 + shift);
+                            else tma_load_2d_2cta(sa, &map_a2, full, (cb - p.kb1) * p.BK, m0);
+                            tma_load_2d_2cta(sb, &map_b, full, kb * p.BK, n0);
+                        } else {
+                            if (p.s2) {
+                                tma_load_4d(sa, &map_a1, full, cb * p.BK, 2 * tx * p.BW + s, 2 * ty * p.BH + r, bi * p.BI);
+                            } else if (cb < p.kb1) {
+                                const int shift = (p.taps == 9) ? (r - 1) * p.in_PW + (s - 1) : 0;
+                                tma_load_2d(sa, &map_a1, full, cb * p.BK, m0 + shift);
+                            } else {
+                                tma_load_2d(sa, &map_a2, full, (cb - p.kb1) * p.BK, m0);
+                            }
+                            tma_load_2d(sb, &map_b, full, kb * p.BK, n0);
+                        }
+                        if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
                     }
-                    tma_load_2d(sb, &map_b, full, kb * p.BK, n0);
-                    if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
                 }
             }
         }
@@ -304,19 +314,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                 mbar_wait(smem_u32(&ctl->acc_empty[as]), aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * kAccStride;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                for (int kb0 = 0; kb0 < num_kb; kb0 += p.kbs, ++it) {
+                    const int nkb = min(p.kbs, num_kb - kb0);
                     const uint32_t stage = it % p.num_stages, phase = (it / p.num_stages) & 1;
                     mbar_wait(smem_u32(&ctl->full[stage]), phase);
                     tc_fence_after();
-                    const uint32_t sa = ring + stage * stage_bytes, sb = sa + p.a_bytes;
-                    const uint64_t adesc = make_smem_desc(sa, p.sbo_bytes, p.layout_type);
-                    const uint64_t bdesc = make_smem_desc(sb, p.sbo_bytes, p.layout_type);
-                    for (int k = 0; k < mma_per_kb; ++k) {
-                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        if constexpr (CG == 1) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
-                        else umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
+                    for (int j = 0; j < nkb; ++j) {
+                        const uint32_t sa = ring + stage * stage_bytes + j * kb_bytes, sb = sa + p.a_bytes;
+                        const uint64_t adesc = make_smem_desc(sa, p.sbo_bytes, p.layout_type);
+                        const uint64_t bdesc = make_smem_desc(sb, p.sbo_bytes, p.layout_type);
+                        for (int k = 0; k < mma_per_kb; ++k) {
+                            if (p.dbg & 4) break;
+                            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+                            if constexpr (CG == 1) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb0 | j | k) != 0);
+                            else umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb0 | j | k) != 0);
+                        }
                     }
-                    // frees the smem slot (in both CTAs when CG = 2) once these MMAs retire
+                    // one commit per stage: frees the smem slot (in both CTAs when CG = 2) once these MMAs retire.  A commit
+                    // after only 4 MMAs leaves the tensor pipe idle ~200 cycles (tools/micro/mma_rate.cu), hence kbs = 2.
                     if constexpr (CG == 1) umma_commit(smem_u32(&ctl->empty[stage]));
                     else umma_commit_2cta(smem_u32(&ctl->empty[stage]));
                 }
@@ -388,6 +403,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quad * 32) << 16);
             for (int ch = hsel; ch < nchunks; ch += 2) {
+                if (p.dbg & 2) break;
                 const int c0 = ch * CH;                  // column inside the tile
                 uint32_t raw[32];
                 if (f32out) tmem_ld16(taddr + c0, raw); else tmem_ld32(taddr + c0, raw);
@@ -574,6 +590,8 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     static const int cg_env = getenv("BYOLO_CG") ? atoi(getenv("BYOLO_CG")) : 0;     // 1 = force off, 2 = default policy
     p.cg = (cg_env != 1 && q.k == 3 && q.stride == 1 && p.BN >= 128 && p.BK == 64) ? 2 : 1;
     p.b_rows = p.BN / p.cg;
+    static const int dbg_env = getenv("BYOLO_DBG") ? atoi(getenv("BYOLO_DBG")) : 0;
+    p.dbg = dbg_env;
     p.in_PW = g.PW();
     p.s2 = q.stride == 2;
     p.gout.S = g.S;
@@ -591,8 +609,12 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for a CTA pair)
     p.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((kTileM * p.cg) >> 4) << 24);
     const int budget = 227 * 1024 - 1024 - (int)sizeof(SmemCtl) - kEpiWarps * kStageOutBytes - 64;
-    p.num_stages = std::max(2, std::min(kMaxStages, budget / (p.a_bytes + p.b_bytes)));
-    L->smem_bytes = p.num_stages * (p.a_bytes + p.b_bytes) + 1024 + sizeof(SmemCtl) + kEpiWarps * kStageOutBytes + 64;
+    static const int kbs_env = getenv("BYOLO_KBS") ? atoi(getenv("BYOLO_KBS")) : 0;
+    const int num_kb = p.taps * (p.kb1 + p.kb2);
+    p.kbs = (kbs_env == 1 || num_kb < 2 || budget / (2 * (p.a_bytes + p.b_bytes)) < 3) ? 1 : 2;   // >= 3 stages of 2 K blocks
+    const int stage_bytes = p.kbs * (p.a_bytes + p.b_bytes);
+    p.num_stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
+    L->smem_bytes = p.num_stages * stage_bytes + 1024 + sizeof(SmemCtl) + kEpiWarps * kStageOutBytes + 64;
 
     const uint32_t one[5] = {1, 1, 1, 1, 1};
     if (!p.s2) {

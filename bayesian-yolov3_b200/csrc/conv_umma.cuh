@@ -7,6 +7,7 @@ namespace byolo {
 struct UmmaParams {
     int num_m_tiles, num_n_tiles, num_tiles;
     int BN, BK, num_stages;
+    int kbs;                       // K blocks per pipeline stage (1 or 2): one barrier round trip / tcgen05.commit per stage
     int cg;                        // CTAs per tile: 1, or 2 (cta_group::2 pair, M = 256)
     int b_rows;                    // rows of B each CTA stages (BN / cg)
     int a_bytes, b_bytes;          // bytes of one A / B stage tile
@@ -19,6 +20,7 @@ struct UmmaParams {
     Epilogue ep;
     uint32_t idesc;                // tcgen05 instruction descriptor
     uint32_t sbo_bytes, layout_type;
+    int dbg;                       // experiments only (BYOLO_DBG): 1 = no operand TMA loads, 2 = no epilogue work, 4 = no MMAs
     unsigned long long* clk;       // profiling: {clock64, globaltimer} at start and end of CTA 0 (effective SM clock), or null
 };
 

@@ -128,6 +128,49 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a converged warp (elect.sync): tcgen05/TMA operands live in uniform registers, so issuing from a
+// divergent `lane == 0` branch makes the compiler wrap every instruction in an ELECT/R2UR.BROADCAST loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// MMA with the smem descriptors given as (low word, shared high word): only the start-address field changes per call.
+template <int CG>
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b64 da, db;\n"
+            "mov.b64 da, {%1, %3};\n"
+            "mov.b64 db, {%2, %3};\n"
+            "setp.ne.b32 p, %5, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+            "}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b64 da, db;\n"
+            "mov.b64 da, {%1, %3};\n"
+            "mov.b64 db, {%2, %3};\n"
+            "setp.ne.b32 p, %5, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n"
+            "}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -254,35 +297,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     }
 
     if (warp == 0) {
-        // ================================ TMA producer ================================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
-                const int m_tile = (tile / p.num_n_tiles) * CG + (int)rank;
-                const int n0 = (tile % p.num_n_tiles) * p.BN + (int)rank * p.b_rows * (CG - 1);   // CG = 2: my half of B
-                int m0 = m_tile * kTileM, tx = 0, ty = 0, bi = 0;
-                if (p.s2) {
-                    tx = m_tile % p.tiles_x;
-                    ty = (m_tile / p.tiles_x) % p.tiles_y;
-                    bi = m_tile / (p.tiles_x * p.tiles_y);
+        // ================================ TMA producer (whole warp converged, one elected lane issues) ================
+        uint32_t it = 0;
+        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+            const int m_tile = (tile / p.num_n_tiles) * CG + (int)rank;
+            const int n0 = (tile % p.num_n_tiles) * p.BN + (int)rank * p.b_rows * (CG - 1);   // CG = 2: my half of B
+            int m0 = m_tile * kTileM, tx = 0, ty = 0, bi = 0;
+            if (p.s2) {
+                tx = m_tile % p.tiles_x;
+                ty = (m_tile / p.tiles_x) % p.tiles_y;
+                bi = m_tile / (p.tiles_x * p.tiles_y);
+            }
+            int tap = 0, cb = 0;
+            for (int kb0 = 0; kb0 < num_kb; kb0 += p.kbs, ++it) {
+                const int nkb = min(p.kbs, num_kb - kb0);
+                const uint32_t stage = it % p.num_stages, phase = (it / p.num_stages) & 1;
+                mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1);
+                const uint32_t full = smem_u32(&ctl->full[stage]);
+                const bool leader_lane = elect_one();
+                if (p.dbg & 1) {                       // experiment: barrier traffic without any bytes moving
+                    if (leader_lane && rank == 0) mbar_arrive(full);
+                    for (int j = 0; j < nkb; ++j)
+                        if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
+                    __syncwarp();
+                    continue;
                 }
-                int tap = 0, cb = 0;
-                for (int kb0 = 0; kb0 < num_kb; kb0 += p.kbs, ++it) {
-                    const int nkb = min(p.kbs, num_kb - kb0);
-                    const uint32_t stage = it % p.num_stages, phase = (it / p.num_stages) & 1;
-                    mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1);
-                    const uint32_t full = smem_u32(&ctl->full[stage]);
-                    if (p.dbg & 1) {                   // experiment: barrier traffic without any bytes moving
-                        if (rank == 0) mbar_arrive(full);
-                        for (int j = 0; j < nkb; ++j)
-                            if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
-                        continue;
-                    }
-                    if (rank == 0) mbar_expect_tx(full, kb_bytes * nkb * CG);   // bytes of both CTAs land on the leader's barrier
-                    for (int j = 0; j < nkb; ++j) {
-                        const int kb = kb0 + j;
-                        const uint32_t sa = ring + stage * stage_bytes + j * kb_bytes, sb = sa + p.a_bytes;
-                        const int r = tap / 3, s = tap - 3 * r;
+                if (leader_lane && rank == 0) mbar_expect_tx(full, kb_bytes * nkb * CG);   // bytes of both CTAs land on the leader's barrier
+                for (int j = 0; j < nkb; ++j) {
+                    const int kb = kb0 + j;
+                    const uint32_t sa = ring + stage * stage_bytes + j * kb_bytes, sb = sa + p.a_bytes;
+                    const int r = tap / 3, s = tap - 3 * r;
+                    if (leader_lane) {
                         if constexpr (CG == 2) {
                             const int shift = (p.taps == 9) ? (r - 1) * p.in_PW + (s - 1) : 0;
                             if (cb < p.kb1) tma_load_2d_2cta(sa, &map_a1, full, cb * p.BK, m0 + shift);
@@ -299,16 +344,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                             }
                             tma_load_2d(sb, &map_b, full, kb * p.BK, n0);
                         }
-                        if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
                     }
+                    if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer (leader CTA only when CG = 2) ================================
-        if (lane == 0 && rank == 0) {
+        // ================================ MMA issuer (leader CTA only when CG = 2; warp converged, one lane issues) ====
+        if (rank == 0) {
             uint32_t it = 0, tile_it = 0;
-            const int mma_per_kb = p.BK / 16;
+            const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, p.sbo_bytes, p.layout_type) >> 32);
+            const uint32_t lo_fixed = 1u << 16;                      // leading-dimension field (unused for swizzled K-major)
             for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++tile_it) {
                 const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
                 mbar_wait(smem_u32(&ctl->acc_empty[as]), aphase ^ 1);
@@ -319,25 +366,33 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                     const uint32_t stage = it % p.num_stages, phase = (it / p.num_stages) & 1;
                     mbar_wait(smem_u32(&ctl->full[stage]), phase);
                     tc_fence_after();
-                    for (int j = 0; j < nkb; ++j) {
-                        const uint32_t sa = ring + stage * stage_bytes + j * kb_bytes, sb = sa + p.a_bytes;
-                        const uint64_t adesc = make_smem_desc(sa, p.sbo_bytes, p.layout_type);
-                        const uint64_t bdesc = make_smem_desc(sb, p.sbo_bytes, p.layout_type);
-                        for (int k = 0; k < mma_per_kb; ++k) {
-                            if (p.dbg & 4) break;
-                            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-                            if constexpr (CG == 1) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb0 | j | k) != 0);
-                            else umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb0 | j | k) != 0);
+                    if (elect_one()) {
+                        for (int j = 0; j < nkb; ++j) {
+                            const uint32_t sa = ring + stage * stage_bytes + j * kb_bytes;
+                            const uint32_t a_lo = ((sa >> 4) & 0x3FFF) | lo_fixed, b_lo = (((sa + p.a_bytes) >> 4) & 0x3FFF) | lo_fixed;
+                            if (!(p.dbg & 4)) {
+                                // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+                                umma_f16_lohi<CG>(d_tmem, a_lo, b_lo, desc_hi, p.idesc, (kb0 | j) != 0);
+                                umma_f16_lohi<CG>(d_tmem, a_lo + 2, b_lo + 2, desc_hi, p.idesc, 1);
+                                if (p.BK == 64) {
+                                    umma_f16_lohi<CG>(d_tmem, a_lo + 4, b_lo + 4, desc_hi, p.idesc, 1);
+                                    umma_f16_lohi<CG>(d_tmem, a_lo + 6, b_lo + 6, desc_hi, p.idesc, 1);
+                                }
+                            }
                         }
+                        // one commit per stage: frees the smem slot (in both CTAs when CG = 2) once these MMAs retire.  A
+                        // commit after only 4 MMAs leaves the tensor pipe idle ~200 cycles (tools/micro), hence kbs = 2.
+                        if constexpr (CG == 1) umma_commit(smem_u32(&ctl->empty[stage]));
+                        else umma_commit_2cta(smem_u32(&ctl->empty[stage]));
                     }
-                    // one commit per stage: frees the smem slot (in both CTAs when CG = 2) once these MMAs retire.  A commit
-                    // after only 4 MMAs leaves the tensor pipe idle ~200 cycles (tools/micro/mma_rate.cu), hence kbs = 2.
-                    if constexpr (CG == 1) umma_commit(smem_u32(&ctl->empty[stage]));
-                    else umma_commit_2cta(smem_u32(&ctl->empty[stage]));
+                    __syncwarp();
                 }
                 // accumulator complete -> epilogue(s)
-                if constexpr (CG == 1) umma_commit(smem_u32(&ctl->acc_full[as]));
-                else umma_commit_2cta(smem_u32(&ctl->acc_full[as]));
+                if (elect_one()) {
+                    if constexpr (CG == 1) umma_commit(smem_u32(&ctl->acc_full[as]));
+                    else umma_commit_2cta(smem_u32(&ctl->acc_full[as]));
+                }
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {

@@ -12,7 +12,8 @@
 //             the image over all candidates (exact either way);
 //          1. keys -> smem as (ordered score bits : u32, index : u16), bitonic sort of the padded power of two;
 //          2. batches of 512 candidates in sorted order: (A) test against the boxes kept so far, (B) 512x512
-//             suppression bit-matrix inside the batch, (C) one warp resolves the batch sequentially with ballots;
+//             suppression bit-matrix inside the batch, one ballot per 32 pairs, (C) candidates without a possible
+//             suppressor or victim inside the batch are kept outright, one warp walks the others sequentially;
 //          3. gather the kept rows, zero-fill the tail, write indices and count.
 // Because "any earlier kept box overlaps" is order independent, the parallel evaluation selects exactly the boxes
 // the sequential algorithm selects.
@@ -33,26 +34,36 @@ __device__ __forceinline__ uint32_t ordered_key(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-struct BoxA { float ymin, xmin, ymax, xmax, area; };
-constexpr size_t kAuxBytes = sizeof(BoxA) * (kBatch + kMaxOut) + 4u * (kBatch * kWords + kWords) + 4u * kMaxOut;
+// Boxes are kept as (ymin, xmin, ymax, xmax) + area.  A box whose area is <= 0 never overlaps anything in TF's IoU
+// (it returns 0 before looking at the other box); it is stored as (+inf, +inf, -inf, -inf) so that the first
+// interval test of iou_gt rejects it without a separate area check.
+struct __align__(16) Box4 { float ymin, xmin, ymax, xmax; };
+constexpr size_t kAuxBytes = (sizeof(Box4) + 4) * (kBatch + kMaxOut) + 4u * (kBatch * kWords + 8 * kWords) + 4u * kMaxOut;
 
-__device__ __forceinline__ BoxA load_box(const float* r) {
-    BoxA b;
-    b.ymin = fminf(r[0], r[2]);
-    b.xmin = fminf(r[1], r[3]);
-    b.ymax = fmaxf(r[0], r[2]);
-    b.xmax = fmaxf(r[1], r[3]);
-    b.area = __fmul_rn(__fsub_rn(b.ymax, b.ymin), __fsub_rn(b.xmax, b.xmin));
-    return b;
+__device__ __forceinline__ void load_box(const float* r, Box4* b, float* area) {
+    Box4 t;
+    t.ymin = fminf(r[0], r[2]);
+    t.xmin = fminf(r[1], r[3]);
+    t.ymax = fmaxf(r[0], r[2]);
+    t.xmax = fmaxf(r[1], r[3]);
+    const float a = __fmul_rn(__fsub_rn(t.ymax, t.ymin), __fsub_rn(t.xmax, t.xmin));
+    if (!(a > 0.f)) {
+        t.ymin = t.xmin = __int_as_float(0x7f800000);
+        t.ymax = t.xmax = __int_as_float(0xff800000);
+    }
+    *b = t;
+    *area = a;
 }
 
-__device__ __forceinline__ bool iou_gt(const BoxA& a, const BoxA& b, float thr) {
-    if (a.area <= 0.f || b.area <= 0.f) return false;
-    const float ih = fmaxf(__fsub_rn(fminf(a.ymax, b.ymax), fmaxf(a.ymin, b.ymin)), 0.f);
-    const float iw = fmaxf(__fsub_rn(fminf(a.xmax, b.xmax), fmaxf(a.xmin, b.xmin)), 0.f);
+// IoU(a, b) > thr (thr >= 0) with TF's fp32 operation order.  Disjoint boxes (the common case) leave after one or two
+// interval tests: their intersection is 0, hence IoU = 0 <= thr.
+__device__ __forceinline__ bool iou_gt(const Box4& a, float area_a, const Box4& b, float area_b, float thr) {
+    const float ih = __fsub_rn(fminf(a.ymax, b.ymax), fmaxf(a.ymin, b.ymin));
+    if (!(ih > 0.f)) return false;
+    const float iw = __fsub_rn(fminf(a.xmax, b.xmax), fmaxf(a.xmin, b.xmin));
+    if (!(iw > 0.f)) return false;
     const float inter = __fmul_rn(ih, iw);
-    if (inter == 0.f) return false;                       // IoU == 0 exactly; skips the division for disjoint boxes
-    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter)) > thr;
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter)) > thr;
 }
 
 constexpr int kTopK = 4096;          // candidates sorted on the fast path
@@ -93,11 +104,16 @@ nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float 
     uint16_t* key_lo = reinterpret_cast<uint16_t*>(sm + region0);       // [NP]
     uint16_t* hist = reinterpret_cast<uint16_t*>(sm);                   // [kBins] (N <= 32768 < 65536 fits u16)
     uint8_t* aux = sm;
-    BoxA* cand = reinterpret_cast<BoxA*>(aux);                          // [kBatch]
-    BoxA* kept = cand + kBatch;                                         // [max_out]
-    uint32_t* mask = reinterpret_cast<uint32_t*>(kept + kMaxOut);       // [kBatch][kWords]
-    uint32_t* dead = mask + kBatch * kWords;                            // [kWords]
-    int* kept_idx = reinterpret_cast<int*>(dead + kWords);              // [max_out]
+    Box4* cand = reinterpret_cast<Box4*>(aux);                          // [kBatch]
+    Box4* kept = cand + kBatch;                                         // [max_out]
+    float* cand_area = reinterpret_cast<float*>(kept + kMaxOut);        // [kBatch]
+    float* kept_area = cand_area + kBatch;                              // [max_out]
+    uint32_t* mask = reinterpret_cast<uint32_t*>(kept_area + kMaxOut);  // [kBatch][kWords] row k: later candidates k suppresses
+    uint32_t* dead = mask + kBatch * kWords;                            // [kWords] suppressed by earlier batches / padding
+    uint32_t* contested = dead + kWords;                                // [kWords] has a potential suppressor inside the batch
+    uint32_t* has_row = contested + kWords;                             // [kWords] suppresses somebody inside the batch
+    uint32_t* selw = has_row + kWords;                                  // [kWords] final selection of the batch
+    int* kept_idx = reinterpret_cast<int*>(selw + 5 * kWords);          // [max_out]
     __shared__ int s_kept, s_cut_bin, s_ncand, s_fill;
     __shared__ int s_warp_sum[32];
 
@@ -174,64 +190,99 @@ nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float 
             if (kept_before >= max_out) break;
             const int nb = min(kBatch, n_cand - base);
             if (tid < kBatch) {
-                BoxA b;
-                b.ymin = b.xmin = b.ymax = b.xmax = 0.f;
-                b.area = -1.f;
-                if (tid < nb) b = load_box(rows + (size_t)key_lo[base + tid] * D);
+                Box4 b;
+                float a = -1.f;
+                b.ymin = b.xmin = __int_as_float(0x7f800000);
+                b.ymax = b.xmax = __int_as_float(0xff800000);
+                if (tid < nb) load_box(rows + (size_t)key_lo[base + tid] * D, &b, &a);
                 cand[tid] = b;
+                cand_area[tid] = a;
             }
-            if (tid < kWords) dead[tid] = 0u;
+            if (tid < kWords) { dead[tid] = 0u; contested[tid] = 0u; has_row[tid] = 0u; }
             __syncthreads();
             {   // (A) two threads per candidate, each scanning half of the kept list
                 const int c = tid & (kBatch - 1), part = tid >> 9;
                 const int half = (kept_before + 1) >> 1;
                 const int j0 = part * half, j1 = min(kept_before, j0 + half);
-                const BoxA me = cand[c];
+                const Box4 me = cand[c];
+                const float my_area = cand_area[c];
                 bool hit = false;
                 if (c < nb)
                     for (int j = j0; j < j1; ++j)
-                        if (iou_gt(me, kept[j], thr)) { hit = true; break; }
+                        if (iou_gt(me, my_area, kept[j], kept_area[j], thr)) { hit = true; break; }
                 if (hit || c >= nb) atomicOr(&dead[c >> 5], 1u << (c & 31));
             }
             __syncthreads();
-            // (B) mask[k][w] bit i: candidate (32w+i) > k is suppressed by candidate k
-            for (int wid = tid; wid < kBatch * kWords; wid += kNmsThreads) {
-                const int k = wid / kWords, w = wid - k * kWords;
-                uint32_t bits = 0u;
-                if (w * 32 + 31 > k && !((dead[k >> 5] >> (k & 31)) & 1u)) {
-                    const BoxA bk = cand[k];
-                    const uint32_t dw = dead[w];
-                    for (int i = 0; i < 32; ++i) {
-                        const int c = w * 32 + i;
-                        if (c > k && !((dw >> i) & 1u) && iou_gt(cand[c], bk, thr)) bits |= 1u << i;
-                    }
+            // (B) suppression matrix, one ballot per 32 pairs: row k, word w, lane l <-> candidate c = 32w + l
+            for (int k = warp; k < kBatch; k += kNmsThreads / 32) {
+                const bool k_alive = !((dead[k >> 5] >> (k & 31)) & 1u);
+                const int w0 = k >> 5;
+                if (lane < w0 || !k_alive) mask[k * kWords + (lane & (kWords - 1))] = 0u;
+                if (!k_alive) continue;                                  // warp-uniform
+                const Box4 bk = cand[k];
+                const float ak = cand_area[k];
+                uint32_t any = 0u;
+                for (int w = w0; w < kWords; ++w) {
+                    const int c = w * 32 + lane;
+                    const bool bit = (c > k) && !((dead[w] >> lane) & 1u) && iou_gt(cand[c], cand_area[c], bk, ak, thr);
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
+                    if (lane == 0) mask[k * kWords + w] = word;
+                    any |= word;
+                    if (word && lane == 0) atomicOr(&contested[w], word);
                 }
-                mask[wid] = bits;
+                if (any && lane == 0) atomicOr(&has_row[k >> 5], 1u << (k & 31));
             }
             __syncthreads();
-            // (C) sequential resolution by one warp: lane l < kWords owns candidates [32l, 32l+32)
+            // (C) resolve.  A candidate that nobody in the batch can suppress and that suppresses nobody is kept without
+            // looking at the order; only the others (bit in `contested` or `has_row`) go through the sequential walk.
             if (warp == 0) {
-                uint32_t alive = (lane < kWords) ? ~dead[lane] : 0u;
+                const uint32_t alive = (lane < kWords) ? ~dead[lane] : 0u;
+                uint32_t walk = (lane < kWords) ? (alive & (contested[lane] | has_row[lane])) : 0u;
+                uint32_t sel = alive & ~walk;
                 uint32_t removed = 0u;
-                int n_new = 0;
                 while (true) {
-                    const uint32_t cur = alive & ~removed;
+                    const uint32_t cur = walk & ~removed;
                     const uint32_t vote = __ballot_sync(0xFFFFFFFFu, cur != 0u);
                     if (!vote) break;
                     const int src = __ffs(vote) - 1;
                     const uint32_t wv = __shfl_sync(0xFFFFFFFFu, cur, src);
                     const int bit = __ffs(wv) - 1;
                     const int k = src * 32 + bit;
-                    if (lane == 0) {
-                        kept[kept_before + n_new] = cand[k];
-                        kept_idx[kept_before + n_new] = key_lo[base + k];
-                    }
-                    ++n_new;
-                    if (kept_before + n_new >= max_out) break;
                     if (lane < kWords) removed |= mask[k * kWords + lane];
-                    if (lane == src) alive &= ~(1u << bit);
+                    if (lane == src) { walk &= ~(1u << bit); sel |= 1u << bit; }
                 }
-                if (lane == 0) s_kept = kept_before + n_new;
+                // cap at max_out in selection order: prefix counts over the 16 words
+                int cnt = __popc(sel), pre = cnt;
+                for (int o = 1; o < kWords; o <<= 1) {
+                    const int v = __shfl_up_sync(0xFFFFFFFFu, pre, o);
+                    if (lane >= o) pre += v;
+                }
+                const int before = pre - cnt;                            // selected in lower words
+                const int room = max_out - kept_before;
+                if (lane < kWords) {
+                    uint32_t keepw = sel;
+                    if (before >= room) keepw = 0u;
+                    else if (before + cnt > room) {                      // keep only the first (room - before) set bits
+                        int need = room - before;
+                        uint32_t t = sel, out = 0u;
+                        while (need-- > 0) { const uint32_t low = t & (0u - t); out |= low; t ^= low; }
+                        keepw = out;
+                    }
+                    selw[lane] = keepw;
+                    selw[kWords + lane] = (uint32_t)min(before, room);  // rank offset of this word
+                }
+                const int total = __shfl_sync(0xFFFFFFFFu, pre, kWords - 1);
+                if (lane == 0) s_kept = kept_before + min(total, room);
+            }
+            __syncthreads();
+            if (tid < kBatch) {                                          // append in order, in parallel
+                const uint32_t wsel = selw[tid >> 5];
+                if ((wsel >> (tid & 31)) & 1u) {
+                    const int pos = kept_before + (int)selw[kWords + (tid >> 5)] + __popc(wsel & ((1u << (tid & 31)) - 1u));
+                    kept[pos] = cand[tid];
+                    kept_area[pos] = cand_area[tid];
+                    kept_idx[pos] = key_lo[base + tid];
+                }
             }
             __syncthreads();
         }
@@ -259,6 +310,7 @@ int launch_nms(const float* rows, int B, int N, int D, int obj_idx, float iou_th
                int* out_count, void*, size_t, cudaStream_t st) {
     BY_REQUIRE(N >= 0 && N <= kMaxN, "NMS kernel handles up to 32768 candidates per image");
     BY_REQUIRE(max_out >= 1 && max_out <= kMaxOut, "max_out must be in [1, 2048]");
+    BY_REQUIRE(iou_thr >= 0.f, "iou_thr must be >= 0");
     BY_REQUIRE(obj_idx >= 4 && obj_idx < D, "obj_idx out of range");
     if (B == 0) return 0;
     int NP = 2;

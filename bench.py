@@ -221,6 +221,14 @@ def main():
         conv_fl = sum(p['flops'] for p in conv)
         step_ms = sum(p['ms'] for p in prof)
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        traffic = None                                  # DRAM bytes of the conv launches of one step, from the committed ncu capture
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'r01', 'ncu_v5_traffic.json')) as f:
+                tj = json.load(f)
+            if B == WORKLOAD['batch_per_gpu'] and tj['conv_launches'] == len(conv):
+                traffic = tj['conv_dram_bytes_per_step']
+        except Exception:
+            pass
         res = {'metric': METRIC, 'value': world * B * K / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': K,
                'warmup': Wm, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                'dtype': 'f16' if args.precision != 'fp32' else 'f32', 'data': 'synthetic',
@@ -235,7 +243,7 @@ def main():
                'gpu_launches': eng.launch_count(B) * K,
                'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (all %d conv launches of a step)' % len(conv),
                             'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                            'peak_source': peak_src, 'traffic': None, 'conv_share_of_step': conv_ms / step_ms if step_ms else None,
+                            'peak_source': peak_src, 'traffic': traffic, 'conv_share_of_step': conv_ms / step_ms if step_ms else None,
                             'flops_per_image': eng.flops_per_image(), 'step_tflops': eng.flops_per_image() * B / (ms / K * 1e-3) / 1e12},
                'breakdown_ms': {k: sum(p['ms'] for p in prof if p['kind'] == k) for k in ('stem', 'conv', 'stack', 'decode', 'nms')}}
         big = [p for p in conv if p['ms'] > 0.3 and p['sm_mhz'] > 0]

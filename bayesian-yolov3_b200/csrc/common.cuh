@@ -117,6 +117,8 @@ int launch_conv_umma(const ConvProblem& p, cudaStream_t st);                 // 
 int launch_conv_simt(const ConvProblem& p, bool act_half, cudaStream_t st);  // conv_simt.cu
 int launch_stem(const float* img, int B, int H, int W, const float* w32 /*[27,32]*/, const float* bias,
                 void* out, bool act_half, cudaStream_t st);                  // conv_simt.cu
+int launch_stem_mma(const float* img, int B, int H, int W, const __half* w16 /*[32,27]*/, const float* bias, void* out,
+                    cudaStream_t st);                                        // stem.cu (fp16 operands, mma.sync)
 int launch_stack(const void* src, void* dst, long long plane_bytes, int B, int T, cudaStream_t st);
 int launch_pack(const float* dense, void* padded, Geom g, bool act_half, cudaStream_t st);
 int launch_unpack(const void* padded, float* dense, Geom g, bool act_half, cudaStream_t st);

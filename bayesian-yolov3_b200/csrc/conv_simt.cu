@@ -130,13 +130,16 @@ template <> __device__ __forceinline__ void st_act16<__half>(__half* p, const fl
 
 // One thread = two horizontally adjacent output pixels x 32 channels: 36 input values and 64 accumulators in
 // registers, weights read as broadcast float4 from shared memory (8 FMAs per shared load), 128-byte stores.
+// T = __half ("fp16-simt", the CUDA-core twin of the tensor-core path): image and weights are rounded to fp16 first,
+// exactly the operands stem.cu feeds to the tensor cores.
 template <typename T>
 __global__ void __launch_bounds__(128)
 stem_kernel(const float* __restrict__ img, int B, int H, int W, const float* __restrict__ w, const float* __restrict__ bias,
             T* __restrict__ out) {
     __shared__ __align__(16) float sw[27 * 32];
     __shared__ float sb[32];
-    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
+    constexpr bool kRound = sizeof(T) == 2;
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = kRound ? __half2float(__float2half_rn(w[i])) : w[i];
     if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
     const int W2 = W >> 1;
@@ -153,7 +156,10 @@ stem_kernel(const float* __restrict__ img, int B, int H, int W, const float* __r
             const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
             const float* p = img + (((long long)b * H + iy) * W + ix) * 3;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) in[r][q][ch] = ok ? __ldg(p + ch) : 0.f;
+            for (int ch = 0; ch < 3; ++ch) {
+                const float v = ok ? __ldg(p + ch) : 0.f;
+                in[r][q][ch] = kRound ? __half2float(__float2half_rn(v)) : v;
+            }
         }
     }
     T* o = out + (((long long)b * (H + 2) + y + 1) * (W + 2) + x + 1) * 32;

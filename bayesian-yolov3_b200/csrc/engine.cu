@@ -342,7 +342,11 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
         if (prof) BY_CUDA(cudaEventRecord(pl->ev[ei++], st));
         if (s.kind == STEP_STEM) {
             const LayerWeights& w = e->weights[0];
-            if (int r = launch_stem(img, pl->B, c.height, c.width, w.w32, w.bias, pl->bufs[s.out_buf].ptr, e->act_half(), st)) return r;
+            if (c.precision == BYOLO_PREC_FP16) {
+                if (int r = launch_stem_mma(img, pl->B, c.height, c.width, w.w16, w.bias, pl->bufs[s.out_buf].ptr, st)) return r;
+            } else if (int r = launch_stem(img, pl->B, c.height, c.width, w.w32, w.bias, pl->bufs[s.out_buf].ptr, e->act_half(), st)) {
+                return r;
+            }
         } else if (s.kind == STEP_STACK) {
             if (int r = launch_stack(s.src, s.dst, s.plane_bytes, pl->B, c.T, st)) return r;
         } else {
@@ -662,15 +666,25 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
             rc = -2;
         }
     };
-    alloc0(&p1, (size_t)g1.rows() * cin1 * es);
+    const bool stem = cin1 == 3;                  // darknet.py:10: the image conv, fed dense fp32 [S,H,W,3] as it is
+    if (stem && !(k == 3 && stride == 1 && cout == 32 && !in2_dev && !residual_dev && !upsample && bn_host && dropout_layer < 0 &&
+                  H % 32 == 0 && W % 32 == 0)) {
+        set_error("byolo_conv_layer: a 3-channel input is only supported as the stem conv (3x3, stride 1, 32 filters, BN)");
+        w.release();
+        return -1;
+    }
+    if (!stem) alloc0(&p1, (size_t)g1.rows() * cin1 * es);
     if (in2_dev) alloc0(&p2, (size_t)g2.rows() * cin2 * es);
     if (residual_dev) alloc0(&pr, (size_t)go.rows() * cout * es);
     alloc0(&po, (size_t)go.rows() * go.C * (dense ? 4 : es));
     if (dense) alloc0((void**)&tmp, (size_t)S * Ho * Wo * go.C * 4);
-    if (!rc) rc = launch_pack(in1_dev, p1, g1, half, st);
+    if (!rc && !stem) rc = launch_pack(in1_dev, p1, g1, half, st);
     if (!rc && in2_dev) rc = launch_pack(in2_dev, p2, g2, half, st);
     if (!rc && residual_dev) rc = launch_pack(residual_dev, pr, go, half, st);
-    if (!rc) {
+    if (!rc && stem) {
+        rc = (precision == BYOLO_PREC_FP16) ? launch_stem_mma(in1_dev, S, H, W, w.w16, w.bias, po, st)
+                                            : launch_stem(in1_dev, S, H, W, w.w32, w.bias, po, half, st);
+    } else if (!rc) {
         ConvProblem p{};
         p.in1 = p1; p.in2 = p2; p.gin = g1; p.c2 = cin2; p.k = k; p.stride = stride;
         p.cout_pad = w.cout_pad; p.w16 = w.w16; p.w32 = w.w32;

@@ -100,7 +100,8 @@ int byolo_decode(byolo_handle h, const float* raw0_dev, const float* raw1_dev, c
 /* Per-layer test hook: one conv (+dropout)+BN+leaky(+residual) (layers.py:545-575, 505-507) on dense fp32 NHWC device
  * arrays, run through the chosen precision path.  in2 (channel concat partner, 1x1 only) and residual may be NULL.
  * kernel HWIO [k,k,cin1+cin2,cout]; bn = {beta,gamma,mean,var}[cout] or NULL with bias[cout] (linear, no leaky).
- * upsample: store with the nearest x2 of layers.py:578-580 ([S,2H,2W,cout]).  dropout_layer < 0: no dropout. */
+ * upsample: store with the nearest x2 of layers.py:578-580 ([S,2H,2W,cout]).  dropout_layer < 0: no dropout.
+ * cin1 == 3 selects the stem kernels (darknet.py:10: 3x3, stride 1, 32 filters, BN; H, W multiples of 32). */
 int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_dev, int32_t S, int32_t H, int32_t W,
                      int32_t cin1, int32_t cin2, int32_t k, int32_t stride, int32_t cout, const float* kernel_host,
                      const float* bn_host, const float* bias_host, const float* residual_dev, int32_t upsample,

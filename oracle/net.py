@@ -96,7 +96,7 @@ class Forward:
             scale = torch.as_tensor(np.asarray(w['gamma']), dtype=self.dtype) * torch.rsqrt(
                 torch.as_tensor(np.asarray(w['var']), dtype=self.dtype) + BN_EPS)
             k = k * scale.view(-1, 1, 1, 1)
-            k = k if idx == 0 else self._round(k)     # the stem runs on fp32 CUDA cores in the engine
+            k = self._round(k)
         elif self.emulate:
             k = self._round(k)
         self._folded[idx] = k
@@ -154,7 +154,7 @@ class Forward:
             if bayes and self.specs[idx]['dropout']:
                 drop = (seed, di[0], image)
                 di[0] += 1
-            out = self.conv(inp if idx == 0 else self._round(inp), idx, drop)   # emulate: operands are stored rounded
+            out = self.conv(self._round(inp), idx, drop)   # emulate: operands are stored rounded (the image too: stem.cu)
             L.append(out)
             fused[idx] = out
             return out

@@ -176,6 +176,7 @@ def ref_conv(x, kernel, bn=None, bias=None, x2=None, residual=None, stride=1, up
 
 CONV_CASES = {
     # name: (S, H, W, c1, c2, k, stride, cout, residual, upsample, dropout, dense)
+    'stem_3_32': (2, 32, 64, 3, 0, 3, 1, 32, False, False, False, False),
     'pw_64_32': (3, 20, 12, 64, 0, 1, 1, 32, False, False, False, False),
     'c3_32_64_sw64': (2, 16, 16, 32, 0, 3, 1, 64, False, False, False, False),
     'c3_64_128_res': (2, 19, 19, 64, 0, 3, 1, 128, True, False, False, False),
@@ -196,6 +197,8 @@ def _conv_case(name):
     S, H, Wd, c1, c2, k, stride, cout, res, up, drop, dense = CONV_CASES[name]
     rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
     x = rng.standard_normal((S, H, Wd, c1)).astype(np.float32)
+    if c1 == 3:
+        x = rng.random((S, H, Wd, 3), dtype=np.float32)          # the stem reads images in [0,1) (dataset_utils.py:6-11)
     x2 = rng.standard_normal((S, H, Wd, c2)).astype(np.float32) if c2 else None
     cin = c1 + c2
     kernel = (rng.standard_normal((k, k, cin, cout)) * np.sqrt(2.0 / (k * k * cin))).astype(np.float32)

@@ -15,6 +15,7 @@
 // allocator, warps 4-11 epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant split the columns); smem ring of `num_stages` {A,B} tiles with
 // full/empty mbarriers; two TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <algorithm>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -222,14 +223,222 @@ struct SmemCtl {
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
     uint32_t tmem_base;
-    uint32_t pad;
-    float bias[kMaxBias];
+    uint32_t pad[3];
+    alignas(16) float bias[kMaxBias];      // read as float4 by the epilogue
 };
+static_assert(offsetof(SmemCtl, bias) % 16 == 0, "bias must be 16-byte aligned");
+
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr); }
+
+template <int CG>
+__device__ __forceinline__ void tma_a2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    if constexpr (CG == 2) tma_load_2d_2cta(dst, map, bar, c0, c1);
+    else tma_load_2d(dst, map, bar, c0, c1);
+}
+
+// ------------------------------------------------------------------------------------------------------ epilogue math
+// One chunk = 32 accumulator columns of one row (thread = TMEM lane = pixel): [dropout] + shift + leaky [+ residual]
+// -> 32 fp16 = 64 output bytes.  Specialised at compile time: the run-time flags of the old generic loop cost more
+// issue slots than the arithmetic.  Dropout: keep iff the element's 16 random bits >= thr16, written as 32-bit
+// compares ((w << 16) >= thr32 for the low half, w >= thr32 for the high half: identical decisions, no extraction),
+// and the mask multiplier goes through one FFMA with the shift.
+struct DropRow {
+    uint32_t group0;         // (elem index of this row's channel 0) >> 3
+    uint32_t t, image;
+};
+
+template <bool DROP, bool RES>
+__device__ __forceinline__ void chunk_f16(const uint32_t (&raw)[32], const float* __restrict__ bias_s, const uint4 (&res)[4],
+                                          uint4 (&o)[4], const Dropout& d, const DropRow& dr, uint32_t group_c) {
+    const uint32_t thr32 = d.thr16 << 16;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float v[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 8 * g), b1 = *reinterpret_cast<const float4*>(bias_s + 8 * g + 4);
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        if constexpr (DROP) {
+            const uint4 r = philox4x32_10(make_uint4(dr.group0 + group_c + (uint32_t)g, (uint32_t)d.layer_id, dr.t, dr.image), d.seed_lo, d.seed_hi);
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float m0 = ((w[i] << 16) >= thr32) ? d.keep_scale : 0.f;
+                const float m1 = (w[i] >= thr32) ? d.keep_scale : 0.f;
+                v[2 * i] = fmaf(__uint_as_float(raw[8 * g + 2 * i]), m0, b[2 * i]);
+                v[2 * i + 1] = fmaf(__uint_as_float(raw[8 * g + 2 * i + 1]), m1, b[2 * i + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[8 * g + j]) + b[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
+        if constexpr (RES) {
+            const __half2* rh = reinterpret_cast<const __half2*>(&res[g]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(rh[j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+            }
+        }
+        __half2* oh = reinterpret_cast<__half2*>(&o[g]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    }
+}
+
+__device__ __forceinline__ void stage_and_store(const CUtensorMap* map_o, uint32_t stg, uint32_t stg_row, uint32_t swz, int lane,
+                                                bool valid, const uint4 (&o)[4], int c, int row0) {
+    if (lane == 0) bulk_wait_read0();        // the previous store of this warp has drained the staging block
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t dst = stg_row + (((uint32_t)j ^ swz) << 4);
+        const uint4 q = valid ? o[j] : make_uint4(0u, 0u, 0u, 0u);      // border pixels stay zero
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map_o, stg, c, row0);
+        bulk_commit();
+    }
+}
+
+// Epilogue of the 8 epilogue warps.  KIND selects the store path and the fused extras (EpiKind in conv_umma.cuh).
+template <int CG, int KIND>
+__device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const UmmaParams& p, SmemCtl* ctl, uint32_t tmem_base,
+                                             uint32_t out_stage, int warp, int lane, uint32_t rank, int first_tile, int tile_step) {
+    constexpr bool kS2 = KIND == EPI_DIRECT;
+    constexpr bool kF32 = KIND == EPI_F32;
+    constexpr bool kDrop = KIND == EPI_F16_DROP;
+    constexpr bool kRes = KIND == EPI_F16_RES;
+    constexpr bool kTma = KIND == EPI_F16 || KIND == EPI_F16_RES || KIND == EPI_F16_DROP || KIND == EPI_F32;
+    constexpr int CH = kF32 ? 16 : 32;
+    const int quad = warp & 3;
+    const int hsel = (warp - 4) >> 2;
+    const Epilogue& ep = p.ep;
+    const int Ho = p.gout.H, Wo = p.gout.W, S = p.gout.S;
+    const int nchunks = p.BN / CH;
+    const int nnt_shift = p.nnt_shift, BN = p.BN, ldc = ep.ldc;
+    const uint32_t stg = out_stage + (uint32_t)(warp - 4) * kStageOutBytes;
+    const uint32_t stg_row = stg + lane * 64;
+    const uint32_t swz = (uint32_t)((lane >> 1) & 3);
+    const uint32_t acc_full0 = smem_u32(&ctl->acc_full[0]), acc_empty0 = smem_u32(&ctl->acc_empty[0]);
+    const int i = quad * 32 + lane;              // row of the tile == TMEM lane
+    uint32_t tile_it = 0;
+    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++tile_it) {
+        const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
+        const int m_tile = (tile >> nnt_shift) * CG + (int)rank;
+        const int n0 = (tile & ((1 << nnt_shift) - 1)) * BN;
+        int s, y, x;
+        bool valid;
+        uint32_t row = 0;
+        if constexpr (kS2) {
+            const int tx = m_tile % p.tiles_x, ty = (m_tile / p.tiles_x) % p.tiles_y, bi = m_tile / (p.tiles_x * p.tiles_y);
+            const int bw = i % p.BW, bh = (i / p.BW) % p.BH, bn = i / (p.BW * p.BH);
+            s = bi * p.BI + bn;
+            y = ty * p.BH + bh;
+            x = tx * p.BW + bw;
+            valid = (s < S) && (y < Ho) && (x < Wo);
+        } else {
+            // stride 1: the output has the padded geometry of the input, so the GEMM row IS the padded pixel index
+            row = (uint32_t)m_tile * kTileM + (uint32_t)i;
+            const uint32_t su = fdiv(row, p.fd_plane), rem = row - su * p.fd_plane.d;
+            const uint32_t py = fdiv(rem, p.fd_pw), px = rem - py * p.fd_pw.d;
+            s = (int)su;
+            y = (int)py - 1;
+            x = (int)px - 1;
+            valid = (s < S) && (py >= 1u) && ((int)py <= Ho) && (px >= 1u) && ((int)px <= Wo);
+        }
+        DropRow dr{0u, 0u, 0u};
+        if constexpr (kDrop) {
+            const uint32_t im = fdiv((uint32_t)s, p.fd_T);
+            dr.t = (uint32_t)s - im * p.fd_T.d;
+            dr.image = (uint32_t)ep.drop.image0 + im;
+            dr.group0 = ((uint32_t)(y * Wo + x) * (uint32_t)ep.cout + (uint32_t)n0) >> 3;
+        }
+        const __half* res_row = nullptr;
+        uint4 rnext[4] = {};
+        if constexpr (kRes) {
+            res_row = reinterpret_cast<const __half*>(ep.residual) + (size_t)row * ldc + n0;
+            if (valid && hsel < nchunks) {       // first chunk's shortcut values: in flight while the main loop finishes
+                const uint4* rp = reinterpret_cast<const uint4*>(res_row + hsel * CH);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+            }
+        }
+        mbar_wait(acc_full0 + 8 * as, aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quad * 32) << 16);
+#ifdef BYOLO_DBG_HOOKS
+        if (!(p.dbg & 2))
+#endif
+        for (int ch = hsel; ch < nchunks; ch += 2) {
+            const int c0 = ch * CH;                  // column inside the tile
+            uint32_t raw[32];
+            if constexpr (kF32) tmem_ld16(taddr + c0, raw); else tmem_ld32(taddr + c0, raw);
+            uint4 rcur[4] = {};
+            if constexpr (kRes) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+                if (valid && ch + 2 < nchunks) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res_row + (ch + 2) * CH);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+                }
+            }
+            tmem_ld_wait();
+            const int c = n0 + c0;
+            uint4 o4[4];                             // the 64 output bytes of this row
+            if constexpr (kF32) {
+                const float* bs = ctl->bias + c;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b = *reinterpret_cast<const float4*>(bs + 4 * j);
+                    o4[j] = make_uint4(__float_as_uint(__uint_as_float(raw[4 * j]) + b.x), __float_as_uint(__uint_as_float(raw[4 * j + 1]) + b.y),
+                                       __float_as_uint(__uint_as_float(raw[4 * j + 2]) + b.z), __float_as_uint(__uint_as_float(raw[4 * j + 3]) + b.w));
+                }
+            } else {
+                chunk_f16<kDrop, kRes>(raw, ctl->bias + c, rcur, o4, ep.drop, dr, (uint32_t)c0 >> 3);
+            }
+            if constexpr (kTma) {
+                stage_and_store(map_o, stg, stg_row, swz, lane, valid, o4, c, m_tile * kTileM + quad * 32);
+            } else if (valid) {
+                __half* ob = reinterpret_cast<__half*>(ep.out);
+                if constexpr (kS2) {
+                    const size_t opix = ((size_t)s * (Ho + 2) + (y + 1)) * (Wo + 2) + (x + 1);
+                    uint4* o = reinterpret_cast<uint4*>(ob + opix * ldc + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = o4[j];
+                } else {   // EPI_UPSAMPLE: nearest-neighbour x2 -> four destination pixels
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const size_t q = ((size_t)s * (2 * Ho + 2) + (2 * y + dy + 1)) * (2 * Wo + 2) + (2 * x + dx + 1);
+                            uint4* o = reinterpret_cast<uint4*>(ob + q * ldc + c);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) o[j] = o4[j];
+                        }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            if constexpr (CG == 1) mbar_arrive(acc_empty0 + 8 * as);
+            else mbar_arrive_cluster(acc_empty0 + 8 * as, 0);      // the leader's MMA thread waits for both CTAs
+        }
+    }
+    if (kTma && lane == 0) bulk_wait0();          // all output writes complete before the CTA retires
+}
 
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2) works on 256 rows x BN: each CTA stages its own
 // 128 A rows and HALF of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) for both, every CTA runs
 // the epilogue of its own 128 accumulator rows.  Per SM and MMA cycle this moves 2/3 of the bytes of CG = 1.
-template <int CG>
+// S2: stride-2 patch mode (the five downsample convs).
+template <int CG, bool S2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o, const UmmaParams p) {
@@ -244,7 +453,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_kb = p.taps * (p.kb1 + p.kb2);
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
     const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
@@ -278,7 +486,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         }
     }
-    for (int i = threadIdx.x; i < p.num_n_tiles * p.BN; i += kThreads) ctl->bias[i] = __ldg(p.ep.bias + i);
+    for (int i = threadIdx.x; i < (p.BN << p.nnt_shift); i += kThreads) ctl->bias[i] = __ldg(p.ep.bias + i);
     tc_fence_before();
     __syncthreads();
     if constexpr (CG == 2) cluster_sync_all();           // the peer's barriers exist before anyone signals them
@@ -296,101 +504,118 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         p.clk[1] = g;
     }
 
+    // Both control loops below are latency chains of ONE warp: every instruction between two TMA / MMA issues is on the
+    // critical path of the short layers (ncu, profiles/r01: ~1200 cycles per stage with divisions and parameter
+    // re-loads in the loop), so all loop state lives in registers and advances by additions only.
+    const int num_kb = p.taps * (p.kb1 + p.kb2);
+    const int num_stages = p.num_stages, kbs = p.kbs, num_tiles = p.num_tiles, nnt_shift = p.nnt_shift;
+    const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
+
     if (warp == 0) {
         // ================================ TMA producer (whole warp converged, one elected lane issues) ================
-        uint32_t it = 0;
-        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
-            const int m_tile = (tile / p.num_n_tiles) * CG + (int)rank;
-            const int n0 = (tile % p.num_n_tiles) * p.BN + (int)rank * p.b_rows * (CG - 1);   // CG = 2: my half of B
-            int m0 = m_tile * kTileM, tx = 0, ty = 0, bi = 0;
-            if (p.s2) {
-                tx = m_tile % p.tiles_x;
-                ty = (m_tile / p.tiles_x) % p.tiles_y;
-                bi = m_tile / (p.tiles_x * p.tiles_y);
+        const int BK = p.BK, BN = p.BN, kbt = p.kb1 + p.kb2, kb1 = p.kb1, in_PW = p.in_PW;
+        const int row_shift0 = (p.taps == 9) ? -in_PW - 1 : 0;
+        const int n_rank = (int)rank * p.b_rows * (CG - 1);                  // CG = 2: my half of B
+        const uint32_t a_bytes = p.a_bytes;
+        uint32_t stage = 0, phase = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            const int m_tile = (tile >> nnt_shift) * CG + (int)rank;
+            const int n0 = (tile & ((1 << nnt_shift) - 1)) * BN + n_rank;
+            const int m0 = m_tile * kTileM;
+            int x2 = 0, y2 = 0, b2 = 0;
+            if constexpr (S2) {
+                const int tx = m_tile % p.tiles_x, q = m_tile / p.tiles_x;
+                const int ty = q % p.tiles_y;
+                x2 = 2 * tx * p.BW;
+                y2 = 2 * ty * p.BH;
+                b2 = (q / p.tiles_y) * p.BI;
             }
-            int tap = 0, cb = 0;
-            for (int kb0 = 0; kb0 < num_kb; kb0 += p.kbs, ++it) {
-                const int nkb = min(p.kbs, num_kb - kb0);
-                const uint32_t stage = it % p.num_stages, phase = (it / p.num_stages) & 1;
-                mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1);
-                const uint32_t full = smem_u32(&ctl->full[stage]);
+            int cb = 0, r = 0, s = 0;                     // channel block, filter tap (r, s)
+            int a_row = m0 + row_shift0, b_k = 0;
+            for (int kb = 0; kb < num_kb; kb += kbs) {
+                const int nkb = min(kbs, num_kb - kb);
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t full = full0 + 8 * stage;
                 const bool leader_lane = elect_one();
+                uint32_t sa = ring + stage * stage_bytes;
+#ifdef BYOLO_DBG_HOOKS
                 if (p.dbg & 1) {                       // experiment: barrier traffic without any bytes moving
                     if (leader_lane && rank == 0) mbar_arrive(full);
-                    for (int j = 0; j < nkb; ++j)
-                        if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
                     __syncwarp();
+                    if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
                     continue;
                 }
+#endif
                 if (leader_lane && rank == 0) mbar_expect_tx(full, kb_bytes * nkb * CG);   // bytes of both CTAs land on the leader's barrier
                 for (int j = 0; j < nkb; ++j) {
-                    const int kb = kb0 + j;
-                    const uint32_t sa = ring + stage * stage_bytes + j * kb_bytes, sb = sa + p.a_bytes;
-                    const int r = tap / 3, s = tap - 3 * r;
                     if (leader_lane) {
-                        if constexpr (CG == 2) {
-                            const int shift = (p.taps == 9) ? (r - 1) * p.in_PW + (s - 1) : 0;
-                            if (cb < p.kb1) tma_load_2d_2cta(sa, &map_a1, full, cb * p.BK, m0 + shift);
-                            else tma_load_2d_2cta(sa, &map_a2, full, (cb - p.kb1) * p.BK, m0);
-                            tma_load_2d_2cta(sb, &map_b, full, kb * p.BK, n0);
+                        if constexpr (S2) {
+                            tma_load_4d(sa, &map_a1, full, cb * BK, x2 + s, y2 + r, b2);
                         } else {
-                            if (p.s2) {
-                                tma_load_4d(sa, &map_a1, full, cb * p.BK, 2 * tx * p.BW + s, 2 * ty * p.BH + r, bi * p.BI);
-                            } else if (cb < p.kb1) {
-                                const int shift = (p.taps == 9) ? (r - 1) * p.in_PW + (s - 1) : 0;
-                                tma_load_2d(sa, &map_a1, full, cb * p.BK, m0 + shift);
-                            } else {
-                                tma_load_2d(sa, &map_a2, full, (cb - p.kb1) * p.BK, m0);
-                            }
-                            tma_load_2d(sb, &map_b, full, kb * p.BK, n0);
+                            if (cb < kb1) tma_a2d<CG>(sa, &map_a1, full, cb * BK, a_row);
+                            else tma_a2d<CG>(sa, &map_a2, full, (cb - kb1) * BK, a_row);
                         }
+                        tma_a2d<CG>(sa + a_bytes, &map_b, full, b_k, n0);
                     }
-                    if (++cb == p.kb1 + p.kb2) { cb = 0; ++tap; }
+                    sa += kb_bytes;
+                    b_k += BK;
+                    if (++cb == kbt) {                    // next filter tap: one pixel right, or down a row and two left
+                        cb = 0;
+                        if (++s == 3) { s = 0; ++r; a_row += in_PW - 2; } else { ++a_row; }
+                    }
                 }
                 __syncwarp();
+                if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA only when CG = 2; warp converged, one lane issues) ====
         if (rank == 0) {
-            uint32_t it = 0, tile_it = 0;
             const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, p.sbo_bytes, p.layout_type) >> 32);
             const uint32_t lo_fixed = 1u << 16;                      // leading-dimension field (unused for swizzled K-major)
-            for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++tile_it) {
+            const uint32_t idesc = p.idesc, a16 = p.a_bytes >> 4, kb16 = kb_bytes >> 4;
+            const bool bk64 = p.BK == 64;
+            const uint32_t acc_full0 = smem_u32(&ctl->acc_full[0]), acc_empty0 = smem_u32(&ctl->acc_empty[0]);
+            uint32_t stage = 0, phase = 0, tile_it = 0;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++tile_it) {
                 const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
-                mbar_wait(smem_u32(&ctl->acc_empty[as]), aphase ^ 1);
+                mbar_wait(acc_empty0 + 8 * as, aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * kAccStride;
-                for (int kb0 = 0; kb0 < num_kb; kb0 += p.kbs, ++it) {
-                    const int nkb = min(p.kbs, num_kb - kb0);
-                    const uint32_t stage = it % p.num_stages, phase = (it / p.num_stages) & 1;
-                    mbar_wait(smem_u32(&ctl->full[stage]), phase);
+                for (int kb = 0; kb < num_kb; kb += kbs) {
+                    const int nkb = min(kbs, num_kb - kb);
+                    mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     if (elect_one()) {
+                        uint32_t a_lo = ((ring + stage * stage_bytes) >> 4) | lo_fixed;      // smem < 256 KB: the field never overflows
                         for (int j = 0; j < nkb; ++j) {
-                            const uint32_t sa = ring + stage * stage_bytes + j * kb_bytes;
-                            const uint32_t a_lo = ((sa >> 4) & 0x3FFF) | lo_fixed, b_lo = (((sa + p.a_bytes) >> 4) & 0x3FFF) | lo_fixed;
-                            if (!(p.dbg & 4)) {
+#ifdef BYOLO_DBG_HOOKS
+                            if (!(p.dbg & 4))
+#endif
+                            {
                                 // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-                                umma_f16_lohi<CG>(d_tmem, a_lo, b_lo, desc_hi, p.idesc, (kb0 | j) != 0);
-                                umma_f16_lohi<CG>(d_tmem, a_lo + 2, b_lo + 2, desc_hi, p.idesc, 1);
-                                if (p.BK == 64) {
-                                    umma_f16_lohi<CG>(d_tmem, a_lo + 4, b_lo + 4, desc_hi, p.idesc, 1);
-                                    umma_f16_lohi<CG>(d_tmem, a_lo + 6, b_lo + 6, desc_hi, p.idesc, 1);
+                                const uint32_t b_lo = a_lo + a16;
+                                umma_f16_lohi<CG>(d_tmem, a_lo, b_lo, desc_hi, idesc, (kb | j) != 0);
+                                umma_f16_lohi<CG>(d_tmem, a_lo + 2, b_lo + 2, desc_hi, idesc, 1);
+                                if (bk64) {
+                                    umma_f16_lohi<CG>(d_tmem, a_lo + 4, b_lo + 4, desc_hi, idesc, 1);
+                                    umma_f16_lohi<CG>(d_tmem, a_lo + 6, b_lo + 6, desc_hi, idesc, 1);
                                 }
                             }
+                            a_lo += kb16;
                         }
                         // one commit per stage: frees the smem slot (in both CTAs when CG = 2) once these MMAs retire.  A
                         // commit after only 4 MMAs leaves the tensor pipe idle ~200 cycles (tools/micro), hence kbs = 2.
-                        if constexpr (CG == 1) umma_commit(smem_u32(&ctl->empty[stage]));
-                        else umma_commit_2cta(smem_u32(&ctl->empty[stage]));
+                        if constexpr (CG == 1) umma_commit(empty0 + 8 * stage);
+                        else umma_commit_2cta(empty0 + 8 * stage);
                     }
                     __syncwarp();
+                    if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
                 }
                 // accumulator complete -> epilogue(s)
                 if (elect_one()) {
-                    if constexpr (CG == 1) umma_commit(smem_u32(&ctl->acc_full[as]));
-                    else umma_commit_2cta(smem_u32(&ctl->acc_full[as]));
+                    if constexpr (CG == 1) umma_commit(acc_full0 + 8 * as);
+                    else umma_commit_2cta(acc_full0 + 8 * as);
                 }
                 __syncwarp();
             }
@@ -405,155 +630,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         //   * stride-2 / upsampling layers: 16-byte stores straight from registers (rows are not contiguous there).
         // The residual of the next chunk is requested before the current one is processed (the first one before the
         // accumulator barrier), so its latency overlaps TMEM traffic and math.
-        const int quad = warp & 3;
-        const int hsel = (warp - 4) >> 2;
-        const Epilogue& ep = p.ep;
-        const int Ho = p.gout.H, Wo = p.gout.W;
-        const bool f32out = ep.out_mode == OUT_PADDED_F32;
-        const bool tma_out = !p.s2 && ep.out_mode != OUT_UPSAMPLE2;
-        const int CH = f32out ? 16 : 32;
-        const int nchunks = p.BN / CH;
-        const bool has_res = ep.residual != nullptr;
-        const uint32_t stg = out_stage + (uint32_t)(warp - 4) * kStageOutBytes;
-        const uint32_t stg_row = stg + lane * 64;
-        const uint32_t swz = (uint32_t)((lane >> 1) & 3);
-        uint32_t tile_it = 0;
-        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++tile_it) {
-            const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
-            const int m_tile = (tile / p.num_n_tiles) * CG + (int)rank;
-            const int n0 = (tile % p.num_n_tiles) * p.BN;
-            const int i = quad * 32 + lane;              // row of the tile == TMEM lane
-            int s, y, x;
-            bool valid;
-            if (p.s2) {
-                const int tx = m_tile % p.tiles_x, ty = (m_tile / p.tiles_x) % p.tiles_y, bi = m_tile / (p.tiles_x * p.tiles_y);
-                const int bw = i % p.BW, bh = (i / p.BW) % p.BH, bn = i / (p.BW * p.BH);
-                s = bi * p.BI + bn;
-                y = ty * p.BH + bh;
-                x = tx * p.BW + bw;
-                valid = (s < p.gout.S) && (y < Ho) && (x < Wo);
-            } else {
-                const long long row = (long long)m_tile * kTileM + i;
-                const int plane = (Ho + 2) * (Wo + 2);
-                s = (int)(row / plane);
-                const int rem = (int)(row - (long long)s * plane);
-                const int py = rem / (Wo + 2), px = rem - py * (Wo + 2);
-                y = py - 1;
-                x = px - 1;
-                valid = (s < p.gout.S) && (py >= 1) && (py <= Ho) && (px >= 1) && (px <= Wo);
-            }
-            const long long opix_padded = ((long long)s * (Ho + 2) + (y + 1)) * (Wo + 2) + (x + 1);
-            const uint32_t elem_pix = (uint32_t)(y * Wo + x) * (uint32_t)ep.cout;      // dropout element index base
-            const int t_smp = ep.drop.enabled ? (s % ep.drop.T) : 0;
-            const int image = ep.drop.enabled ? (ep.drop.image0 + s / ep.drop.T) : 0;
-            const __half* res_row = reinterpret_cast<const __half*>(ep.residual) + opix_padded * ep.ldc + n0;
-
-            uint4 rnext[4];
-            if (has_res && valid && hsel < nchunks) {
-                const uint4* rp = reinterpret_cast<const uint4*>(res_row + hsel * CH);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
-            }
-            mbar_wait(smem_u32(&ctl->acc_full[as]), aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quad * 32) << 16);
-            for (int ch = hsel; ch < nchunks; ch += 2) {
-                if (p.dbg & 2) break;
-                const int c0 = ch * CH;                  // column inside the tile
-                uint32_t raw[32];
-                if (f32out) tmem_ld16(taddr + c0, raw); else tmem_ld32(taddr + c0, raw);
-                uint4 rcur[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-                if (has_res && valid && ch + 2 < nchunks) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res_row + (ch + 2) * CH);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
-                }
-                tmem_ld_wait();
-                const int c = n0 + c0;
-                uint4 o4[4];                             // the 64 output bytes of this row
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {            // groups of 16 accumulator columns (one group if fp32 output)
-                    if (g == 1 && f32out) break;
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[g * 16 + j]);
-                    const int cg = c + g * 16;
-                    if (ep.drop.enabled) {
-                        dropout8(v, ep.drop, (elem_pix + (uint32_t)cg) >> 3, t_smp, image);
-                        dropout8(v + 8, ep.drop, ((elem_pix + (uint32_t)cg) >> 3) + 1, t_smp, image);
+        if constexpr (S2) {
+            run_epilogue<CG, EPI_DIRECT>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
+        } else {
+            switch (p.epi_kind) {
+                case EPI_F16: run_epilogue<CG, EPI_F16>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+                case EPI_F16_RES: run_epilogue<CG, EPI_F16_RES>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+                case EPI_F16_DROP: run_epilogue<CG, EPI_F16_DROP>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+                default:
+                    if constexpr (CG == 1) {
+                        if (p.epi_kind == EPI_F32) run_epilogue<CG, EPI_F32>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
+                        else run_epilogue<CG, EPI_UPSAMPLE>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
                     }
-                    const float* bs = ctl->bias + cg;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] += bs[j];
-                        if (ep.leaky) v[j] = fmaxf(v[j], 0.1f * v[j]);
-                    }
-                    if (f32out) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            o4[j] = valid ? make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                                                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]))
-                                          : make_uint4(0u, 0u, 0u, 0u);
-                    } else {
-                        if (has_res) {
-                            const __half2* rh = reinterpret_cast<const __half2*>(&rcur[g * 2]);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float2 f = __half22float2(rh[j]);
-                                v[2 * j] += f.x;
-                                v[2 * j + 1] += f.y;
-                            }
-                        }
-                        __half2* oh = reinterpret_cast<__half2*>(&o4[g * 2]);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) oh[j] = valid ? __floats2half2_rn(v[2 * j], v[2 * j + 1]) : __floats2half2_rn(0.f, 0.f);
-                    }
-                }
-                if (tma_out) {
-                    if (lane == 0) bulk_wait_read0();    // the previous store of this warp has drained the staging block
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t dst = stg_row + (((uint32_t)j ^ swz) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o4[j].x), "r"(o4[j].y), "r"(o4[j].z),
-                                     "r"(o4[j].w)
-                                     : "memory");
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&map_o, stg, c, m_tile * kTileM + quad * 32);
-                        bulk_commit();
-                    }
-                } else if (valid) {
-                    __half* ob = reinterpret_cast<__half*>(ep.out);
-                    if (ep.out_mode == OUT_PADDED) {
-                        uint4* o = reinterpret_cast<uint4*>(ob + opix_padded * ep.ldc + c);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) o[j] = o4[j];
-                    } else {   // OUT_UPSAMPLE2: nearest-neighbour x2 -> four destination pixels
-#pragma unroll
-                        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                            for (int dx = 0; dx < 2; ++dx) {
-                                const long long q = ((long long)s * (2 * Ho + 2) + (2 * y + dy + 1)) * (2 * Wo + 2) + (2 * x + dx + 1);
-                                uint4* o = reinterpret_cast<uint4*>(ob + q * ep.ldc + c);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) o[j] = o4[j];
-                            }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (CG == 1) mbar_arrive(smem_u32(&ctl->acc_empty[as]));
-                else mbar_arrive_cluster(smem_u32(&ctl->acc_empty[as]), 0);      // the leader's MMA thread waits for both CTAs
+                    break;
             }
         }
-        if (tma_out && lane == 0) bulk_wait0();          // all output writes complete before the CTA retires
     }
 
     // ---------------- teardown ----------------
@@ -611,6 +702,17 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
     return 0;
 }
 
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{d, 0u, 0u};
+    if (d <= 1) { f.d = 1; return f; }
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) ++lg;                        // ceil(log2 d)
+    const uint32_t pw = 31 + lg;
+    f.mul = (uint32_t)(((1ull << pw) + d - 1) / d);
+    f.shr = pw - 32;
+    return f;
+}
+
 // best (BW, BH, BI) with BW*BH*BI == 128 for a stride-2 output of S x Ho x Wo
 static void pick_patch(int S, int Ho, int Wo, int* BW, int* BH, int* BI) {
     double best = -1;
@@ -641,6 +743,8 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.BN = std::min(q.cout_pad, 256);
     BY_REQUIRE(q.cout_pad % p.BN == 0, "cout_pad must be a multiple of the N tile");
     p.num_n_tiles = q.cout_pad / p.BN;
+    BY_REQUIRE((p.num_n_tiles & (p.num_n_tiles - 1)) == 0, "the number of N tiles must be a power of two");
+    for (p.nnt_shift = 0; (1 << p.nnt_shift) < p.num_n_tiles; ++p.nnt_shift) {}
     // CTA pairs for the feed-bound shapes: 3x3 stride-1 convs with wide N tiles
     static const int cg_env = getenv("BYOLO_CG") ? atoi(getenv("BYOLO_CG")) : 0;     // 1 = force off, 2 = default policy
     p.cg = (cg_env != 1 && q.k == 3 && q.stride == 1 && p.BN >= 128 && p.BK == 64) ? 2 : 1;
@@ -656,6 +760,20 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     if (q.ep.out_mode != OUT_PADDED_F32) BY_REQUIRE(q.ep.cout % 32 == 0 && q.ep.ldc % 32 == 0, "fp16 outputs need cout % 32 == 0");
     else BY_REQUIRE(q.ep.ldc == q.cout_pad && !p.s2, "fp32 (detection) outputs are stored cout_pad wide, stride 1 only");
     p.ep = q.ep;
+    p.ep.drop.thr16 = std::min<uint32_t>(p.ep.drop.thr16, 65535u);
+    if (p.s2) p.epi_kind = EPI_DIRECT;
+    else if (q.ep.out_mode == OUT_PADDED_F32) p.epi_kind = EPI_F32;
+    else if (q.ep.out_mode == OUT_UPSAMPLE2) p.epi_kind = EPI_UPSAMPLE;
+    else if (q.ep.drop.enabled) p.epi_kind = EPI_F16_DROP;
+    else if (q.ep.residual) p.epi_kind = EPI_F16_RES;
+    else p.epi_kind = EPI_F16;
+    BY_REQUIRE((p.epi_kind == EPI_F32) == !q.ep.leaky, "fp16 outputs are conv+BN+leaky layers, the fp32 output is the linear detection conv");
+    BY_REQUIRE(!(q.ep.drop.enabled && (q.ep.residual || p.epi_kind != EPI_F16_DROP)), "dropout only on plain stride-1 convs");
+    BY_REQUIRE(!(q.ep.residual && p.epi_kind != EPI_F16_RES), "residual only on plain stride-1 convs");
+    BY_REQUIRE(g.rows() < (1ll << 31), "activation map too large for 32-bit row indices");
+    p.fd_plane = make_fastdiv((uint32_t)(g.PH() * g.PW()));
+    p.fd_pw = make_fastdiv((uint32_t)g.PW());
+    p.fd_T = make_fastdiv((uint32_t)std::max(q.ep.drop.T, 1));
     const int swz = p.BK * 2;                                     // 128B or 64B rows
     p.sbo_bytes = 8 * swz;
     p.layout_type = (swz == 128) ? 2u : 4u;                       // SWIZZLE_128B / SWIZZLE_64B
@@ -719,9 +837,11 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(conv_umma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            attr_err = cudaFuncSetAttribute(conv_umma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(conv_umma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     BY_CUDA(attr_err);
     return 0;
@@ -744,9 +864,11 @@ int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
         attr[1].val.clusterDim.y = 1;
         attr[1].val.clusterDim.z = 1;
         cfg.numAttrs = 2;
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2>, L.a1, L.a2, L.b, L.o, L.p));
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, false>, L.a1, L.a2, L.b, L.o, L.p));
+    } else if (L.p.s2) {
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, true>, L.a1, L.a2, L.b, L.o, L.p));
     } else {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1>, L.a1, L.a2, L.b, L.o, L.p));
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, false>, L.a1, L.a2, L.b, L.o, L.p));
     }
     return 0;
 }

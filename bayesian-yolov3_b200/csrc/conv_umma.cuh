@@ -4,6 +4,21 @@
 
 namespace byolo {
 
+// epilogue specialisations of conv_umma_kernel (run_epilogue<KIND>)
+enum EpiKind : int {
+    EPI_F16 = 0,        // shift + leaky -> fp16, TMA store (stride-1 convs)
+    EPI_F16_RES = 1,    //   ... + residual shortcut (layers.py:505-507)
+    EPI_F16_DROP = 2,   //   dropout before the shift (layers.py:521-524, 560-570)
+    EPI_F32 = 3,        // + bias, linear -> fp32 raw detection map, TMA store (layers.py:600-613)
+    EPI_DIRECT = 4,     // stride-2 patch tiles: shift + leaky -> fp16, 16-byte stores
+    EPI_UPSAMPLE = 5,   // shift + leaky -> fp16 stored to the four pixels of the nearest x2 upsample (layers.py:578-580)
+};
+
+// n / d for n < 2^31 as umulhi(n, mul) >> shr (d == 1: identity)
+struct FastDiv {
+    uint32_t d, mul, shr;
+};
+
 struct UmmaParams {
     int num_m_tiles, num_n_tiles, num_tiles;
     int BN, BK, num_stages;
@@ -20,7 +35,10 @@ struct UmmaParams {
     Epilogue ep;
     uint32_t idesc;                // tcgen05 instruction descriptor
     uint32_t sbo_bytes, layout_type;
-    int dbg;                       // experiments only (BYOLO_DBG): 1 = no operand TMA loads, 2 = no epilogue work, 4 = no MMAs
+    int epi_kind;                  // EpiKind
+    int nnt_shift;                 // log2(num_n_tiles)
+    FastDiv fd_plane, fd_pw, fd_T; // stride-1 row -> (sample, padded y, padded x); sample -> (image, MC sample t)
+    int dbg;                       // experiments only (-DBYOLO_DBG_HOOKS, BYOLO_DBG): 1 = no operand TMA loads, 2 = no epilogue work, 4 = no MMAs
     unsigned long long* clk;       // profiling: {clock64, globaltimer} at start and end of CTA 0 (effective SM clock), or null
 };
 

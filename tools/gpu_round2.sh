@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out; : > gpurun_out/summary.txt
 echo "=== tests" | tee -a gpurun_out/summary.txt
-timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/tests.log 2>&1; echo "exit $?" | tee -a gpurun_out/summary.txt
+timeout 900 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_out/tests.log 2>&1; echo "exit $?" | tee -a gpurun_out/summary.txt
 tail -n 8 gpurun_out/tests.log | tee -a gpurun_out/summary.txt
 grep -E "^E   .*(Failed|Assertion)" gpurun_out/tests.log | cut -c1-600 | head -20 | tee -a gpurun_out/summary.txt
 echo "=== smoke" | tee -a gpurun_out/summary.txt

@@ -31,21 +31,20 @@ void set_error(const std::string& msg);
     } while (0)
 
 // ----------------------------------------------------------------------------------------------------------
-// Activation layout: "padded NHWC".  A map of S samples x H x W x C is stored as [S, H+2, W+2, C] with an
-// all-zero one-pixel border, so that a 3x3/stride-1 tap is a constant row shift of the flattened
-// [S*(H+2)*(W+2), C] matrix and SAME padding needs no special case.
+// Activation layout: dense NHWC.  A map of S samples x H x W x C is the row-major matrix [S*H*W, C]; GEMM row m is
+// pixel (s, y, x) = (m / (H*W), (m / W) % H, m % W).  SAME / explicit padding is never materialised: the tensor-core
+// path reads its A operand through TMA im2col tensor maps (out-of-image taps are zero-filled by the hardware), the
+// CUDA-core path tests the bounds.
 // ----------------------------------------------------------------------------------------------------------
 struct Geom {
     int S, H, W, C;
-    __host__ __device__ int PW() const { return W + 2; }
-    __host__ __device__ int PH() const { return H + 2; }
-    __host__ __device__ long long rows() const { return (long long)S * PH() * PW(); }
+    __host__ __device__ long long rows() const { return (long long)S * H * W; }
 };
 
 enum OutMode : int {
-    OUT_PADDED = 0,      // T   [S,H+2,W+2,ldc]   same geometry as the (stride-1) input
-    OUT_PADDED_F32 = 1,  // f32 [S,H+2,W+2,ldc]   detection conv -> raw head output, ldc = cout padded to 16
-    OUT_UPSAMPLE2 = 2,   // T   [S,2H+2,2W+2,ldc] nearest x2 (layers.py:578-580) fused into the store
+    OUT_DENSE = 0,       // T   [S,Ho,Wo,ldc]
+    OUT_DENSE_F32 = 1,   // f32 [S,Ho,Wo,ldc]     detection conv -> raw head output, ldc = cout padded to 16
+    OUT_UPSAMPLE2 = 2,   // T   [S,2Ho,2Wo,ldc]   nearest x2 (layers.py:578-580) fused into the store
 };
 
 struct Dropout {
@@ -61,7 +60,7 @@ struct Dropout {
 // Epilogue description shared by the tensor-core and the CUDA-core conv kernels.
 struct Epilogue {
     const float* bias;       // [cout_pad]  BN shift (scale is folded into the weights) or detection bias
-    const void* residual;    // padded T, same geometry as the output, or nullptr
+    const void* residual;    // T, same geometry as the output, or nullptr
     void* out;
     int out_mode;
     int ldc;                 // channels of the output buffer
@@ -101,11 +100,13 @@ __device__ __forceinline__ void dropout8(float* x, const Dropout& d, uint32_t gr
 // Kernel launchers (definitions in the respective .cu files). All return 0 / negative error.
 // ----------------------------------------------------------------------------------------------------------
 struct ConvProblem {
-    // input(s): padded half/float buffers
+    // input(s): dense half/float buffers
     const void* in1;
     const void* in2;         // second K-slice of a 1x1 conv over a channel concat [in1, in2] (layers.py:583-592) or null
-    Geom gin;                // geometry of in1 (C = channels of in1)
+    Geom gin;                // geometry of in1 AS THE CONV SEES IT (S = samples of the output; C = channels of in1)
     int c2;                  // channels of in2
+    int t1, t2;              // MC stacking (layers.py:595-597) without a copy: sample s of the conv reads sample s / t1 of
+                             // in1 (s / t2 of in2); 1 = the buffer holds every sample itself.  1x1 convs only.
     int k, stride;           // 1|3, 1|2
     int cout_pad;            // rows of the weight matrix (multiple of 16)
     const __half* w16;       // [cout_pad, K] K-major, K = k*k*(C1+C2) ordered (tap, channel); BN scale folded
@@ -119,7 +120,6 @@ int launch_stem(const float* img, int B, int H, int W, const float* w32 /*[27,32
                 void* out, bool act_half, cudaStream_t st);                  // conv_simt.cu
 int launch_stem_mma(const float* img, int B, int H, int W, const __half* w16 /*[32,27]*/, const float* bias, void* out,
                     cudaStream_t st);                                        // stem.cu (fp16 operands, mma.sync)
-int launch_stack(const void* src, void* dst, long long plane_bytes, int B, int T, cudaStream_t st);
 int launch_pack(const float* dense, void* padded, Geom g, bool act_half, cudaStream_t st);
 int launch_unpack(const void* padded, float* dense, Geom g, bool act_half, cudaStream_t st);
 
@@ -128,7 +128,7 @@ struct DecodeProblem {
     int B, T;                // images, samples per image (1 unless epistemic)
     int cls_cnt;
     int gh[3], gw[3];        // grids, stride 32/16/8
-    const float* raw[3];     // [B*T, gh(+2), gw(+2), ld] fp32; padded = 1: one-pixel border around each map (engine layout)
+    const float* raw[3];     // [B*T, gh(+2), gw(+2), ld] fp32; padded = 1: one-pixel border around each map (unused by the engine)
     int ld[3];
     int padded;
     float prior_h[9], prior_w[9];

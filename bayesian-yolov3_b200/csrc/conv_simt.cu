@@ -1,8 +1,10 @@
 // CUDA-core kernels: the exact fp32 conv path (precision modes "fp32" / "fp16-simt", used to cross-check the
 // tensor-core kernel layer by layer and to give bit-stable rows to the NMS end-to-end tests), the 3-channel stem
-// conv (K1b), the MC-sample stacking copy, and dense <-> padded-NHWC repacking for the test hooks.
+// conv (K1b) of those two modes, and fp32 <-> activation-type conversion for the test hooks.
 // Same semantics as conv_umma.cu: conv -> [dropout] -> + BN shift -> leaky -> [+ residual]
 // (/root/reference/lib_yolo/layers.py:545-575, :505-507, :521-524).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace byolo {
@@ -17,7 +19,7 @@ template <> __device__ __forceinline__ void st_act<__half>(__half* p, float v) {
 // one thread = one output pixel x 4 consecutive output channels
 template <typename T>
 __global__ void __launch_bounds__(256)
-conv_simt_kernel(const T* __restrict__ in1, const T* __restrict__ in2, Geom g, int c2, int k, int stride, int cout_pad,
+conv_simt_kernel(const T* __restrict__ in1, const T* __restrict__ in2, Geom g, int c2, int t1, int t2, int k, int stride, int cout_pad,
                  const float* __restrict__ w /*[K, cout_pad]*/, Epilogue ep, long long total) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
@@ -30,14 +32,14 @@ conv_simt_kernel(const T* __restrict__ in1, const T* __restrict__ in2, Geom g, i
     const int s = (int)(pix / ((long long)Wo * Ho));
     const int c = cg * 4;
     const int C1 = g.C;
+    const int pad = k / 2;         // 3x3: SAME at stride 1 (Appendix B-1), explicit pad 1 on all sides at stride 2 (layers.py:616-635)
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int kk = 0;
     for (int r = 0; r < k; ++r)
         for (int q = 0; q < k; ++q) {
-            const int py = (k == 3) ? y * stride + r : y + 1;
-            const int px = (k == 3) ? x * stride + q : x + 1;
-            const long long prow = ((long long)s * g.PH() + py) * g.PW() + px;
-            const T* a1 = in1 + prow * C1;
+            const int iy = y * stride + r - pad, ix = x * stride + q - pad;
+            if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) { kk += C1 + (in2 ? c2 : 0); continue; }      // zero padding
+            const T* a1 = in1 + (((long long)(s / t1) * g.H + iy) * g.W + ix) * C1;
             for (int ci = 0; ci < C1; ++ci, ++kk) {
                 const float a = ld_act<T>(a1 + ci);
                 const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)kk * cout_pad + c));
@@ -47,7 +49,7 @@ conv_simt_kernel(const T* __restrict__ in1, const T* __restrict__ in2, Geom g, i
                 acc[3] = fmaf(a, wv.w, acc[3]);
             }
             if (in2) {
-                const T* a2 = in2 + prow * c2;
+                const T* a2 = in2 + (((long long)(s / t2) * g.H + iy) * g.W + ix) * c2;
                 for (int ci = 0; ci < c2; ++ci, ++kk) {
                     const float a = ld_act<T>(a2 + ci);
                     const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)kk * cout_pad + c));
@@ -71,24 +73,24 @@ conv_simt_kernel(const T* __restrict__ in1, const T* __restrict__ in2, Geom g, i
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] = v8[(c - c8) + j];
     }
-    const long long opix = ((long long)s * (Ho + 2) + (y + 1)) * (Wo + 2) + (x + 1);
+    const long long opix = ((long long)s * Ho + y) * Wo + x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (c + j >= ep.cout) break;
         float v = acc[j] + __ldg(ep.bias + c + j);
         if (ep.leaky) v = fmaxf(v, 0.1f * v);
-        if (ep.out_mode == OUT_PADDED_F32) {
+        if (ep.out_mode == OUT_DENSE_F32) {
             reinterpret_cast<float*>(ep.out)[opix * ep.ldc + c + j] = v;
             continue;
         }
         if (ep.residual) v += ld_act<T>(reinterpret_cast<const T*>(ep.residual) + opix * ep.ldc + c + j);
         T* ob = reinterpret_cast<T*>(ep.out);
-        if (ep.out_mode == OUT_PADDED) {
+        if (ep.out_mode == OUT_DENSE) {
             st_act<T>(ob + opix * ep.ldc + c + j, v);
         } else {
             for (int dy = 0; dy < 2; ++dy)
                 for (int dx = 0; dx < 2; ++dx) {
-                    const long long qq = ((long long)s * (2 * Ho + 2) + (2 * y + dy + 1)) * (2 * Wo + 2) + (2 * x + dx + 1);
+                    const long long qq = ((long long)s * (2 * Ho) + (2 * y + dy)) * (2 * Wo) + (2 * x + dx);
                     st_act<T>(ob + qq * ep.ldc + c + j, v);
                 }
         }
@@ -97,15 +99,16 @@ conv_simt_kernel(const T* __restrict__ in1, const T* __restrict__ in2, Geom g, i
 
 int launch_conv_simt(const ConvProblem& p, bool act_half, cudaStream_t st) {
     BY_REQUIRE(p.cout_pad % 4 == 0, "cout_pad % 4");
+    BY_REQUIRE((p.t1 <= 1 && p.t2 <= 1) || p.k == 1, "MC-stacked sources only feed 1x1 convs");
     const int Ho = p.gin.H / p.stride, Wo = p.gin.W / p.stride;
     const long long total = (long long)p.gin.S * Ho * Wo * (p.cout_pad / 4);
     const int grid = (int)((total + 255) / 256);
     if (act_half)
-        conv_simt_kernel<__half><<<grid, 256, 0, st>>>((const __half*)p.in1, (const __half*)p.in2, p.gin, p.c2, p.k,
-                                                       p.stride, p.cout_pad, p.w32, p.ep, total);
+        conv_simt_kernel<__half><<<grid, 256, 0, st>>>((const __half*)p.in1, (const __half*)p.in2, p.gin, p.c2, std::max(p.t1, 1),
+                                                       std::max(p.t2, 1), p.k, p.stride, p.cout_pad, p.w32, p.ep, total);
     else
-        conv_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)p.in1, (const float*)p.in2, p.gin, p.c2, p.k, p.stride,
-                                                      p.cout_pad, p.w32, p.ep, total);
+        conv_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)p.in1, (const float*)p.in2, p.gin, p.c2, std::max(p.t1, 1),
+                                                      std::max(p.t2, 1), p.k, p.stride, p.cout_pad, p.w32, p.ep, total);
     BY_CUDA(cudaGetLastError());
     return 0;
 }
@@ -162,7 +165,7 @@ stem_kernel(const float* __restrict__ img, int B, int H, int W, const float* __r
             }
         }
     }
-    T* o = out + (((long long)b * (H + 2) + y + 1) * (W + 2) + x + 1) * 32;
+    T* o = out + (((long long)b * H + y) * W + x) * 32;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {               // 16 output channels at a time keeps the register count down
         float a0[16], a1[16];
@@ -209,60 +212,36 @@ int launch_stem(const float* img, int B, int H, int W, const float* w32, const f
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// stack_feature_map (layers.py:595-597): dst[b*T + t] = src[b] for t < T.   plane_bytes % 16 == 0.
-// ------------------------------------------------------------------------------------------------------------------
-__global__ void stack_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long plane_v, int T, long long total_v) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_v; i += (long long)gridDim.x * blockDim.x) {
-        const long long b = i / plane_v, off = i - b * plane_v;
-        const uint4 v = __ldg(src + i);
-        for (int t = 0; t < T; ++t) dst[(b * T + t) * plane_v + off] = v;
-    }
-}
-
-int launch_stack(const void* src, void* dst, long long plane_bytes, int B, int T, cudaStream_t st) {
-    BY_REQUIRE(plane_bytes % 16 == 0, "plane size must be a multiple of 16 bytes");
-    const long long plane_v = plane_bytes / 16, total = plane_v * B;
-    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-    stack_kernel<<<grid, 256, 0, st>>>((const uint4*)src, (uint4*)dst, plane_v, T, total);
-    BY_CUDA(cudaGetLastError());
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// dense fp32 [S,H,W,C]  <->  padded T [S,H+2,W+2,C]   (test hooks / activation read-back only)
+// fp32 [S,H,W,C]  <->  activation type T, same dense layout   (test hooks / activation read-back only)
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void pack_kernel(const float* __restrict__ dense, T* __restrict__ padded, Geom g, long long total, int to_padded) {
+__global__ void convert_kernel(const float* __restrict__ f32, T* __restrict__ act, long long total, int to_act) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % g.C);
-        const long long pix = i / g.C;
-        const int x = (int)(pix % g.W), y = (int)((pix / g.W) % g.H), s = (int)(pix / ((long long)g.W * g.H));
-        const long long pi = (((long long)s * g.PH() + y + 1) * g.PW() + x + 1) * g.C + c;
-        if (to_padded)
-            st_act<T>(padded + pi, dense[i]);
+        if (to_act)
+            st_act<T>(act + i, f32[i]);
         else
-            const_cast<float*>(dense)[i] = ld_act<T>(padded + pi);
+            const_cast<float*>(f32)[i] = ld_act<T>(act + i);
     }
 }
 
-int launch_pack(const float* dense, void* padded, Geom g, bool act_half, cudaStream_t st) {
-    const long long total = (long long)g.S * g.H * g.W * g.C;
+int launch_pack(const float* dense, void* act, Geom g, bool act_half, cudaStream_t st) {
+    const long long total = g.rows() * g.C;
     const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
     if (act_half)
-        pack_kernel<__half><<<grid, 256, 0, st>>>(dense, (__half*)padded, g, total, 1);
+        convert_kernel<__half><<<grid, 256, 0, st>>>(dense, (__half*)act, total, 1);
     else
-        pack_kernel<float><<<grid, 256, 0, st>>>(dense, (float*)padded, g, total, 1);
+        convert_kernel<float><<<grid, 256, 0, st>>>(dense, (float*)act, total, 1);
     BY_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_unpack(const void* padded, float* dense, Geom g, bool act_half, cudaStream_t st) {
-    const long long total = (long long)g.S * g.H * g.W * g.C;
+int launch_unpack(const void* act, float* dense, Geom g, bool act_half, cudaStream_t st) {
+    const long long total = g.rows() * g.C;
     const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
     if (act_half)
-        pack_kernel<__half><<<grid, 256, 0, st>>>(dense, (__half*)const_cast<void*>(padded), g, total, 0);
+        convert_kernel<__half><<<grid, 256, 0, st>>>(dense, (__half*)const_cast<void*>(act), total, 0);
     else
-        pack_kernel<float><<<grid, 256, 0, st>>>(dense, (float*)const_cast<void*>(padded), g, total, 0);
+        convert_kernel<float><<<grid, 256, 0, st>>>(dense, (float*)const_cast<void*>(act), total, 0);
     BY_CUDA(cudaGetLastError());
     return 0;
 }

@@ -3,13 +3,18 @@
 // shared memory.  Replaces the Conv2D + FusedBatchNorm + LeakyRelu (+ RandomUniform/Floor/Mul dropout, + Add) node
 // groups that /root/reference/lib_yolo/layers.py:545-575 (conv), :505-507 (residual), :521-524 (dropout) create.
 //
-// GEMM view:  D[M = pixels, N = cout] = A[M, K] * W[N, K]^T,  K = taps * (C1 + C2), fp16 operands, fp32 accumulate.
-//   * stride 1: activations live in the padded-NHWC layout (common.cuh), so the A tile of filter tap (r,s) is the
-//     2D box rows [m0 + (r-1)*(W+2) + (s-1), +128) x channels [c0, c0+BK) of the flattened [rows, C] matrix: one
-//     plain 2D TMA load, no im2col buffer.  Border rows of the output are never stored (they stay zero).
-//   * stride 2 (5 darknet downsample layers, layers.py:616-635): the M tile is a BW x BH x BI patch of output
-//     pixels, loaded with a 4D TMA box over [C, W+2, H+2, S] with element strides (1,2,2,1).
-//   * a 1x1 conv over a channel concat [in1, in2] (route, layers.py:583-592) reads its K range from two maps.
+// GEMM view:  D[M = output pixels, N = cout] = A[M, K] * W[N, K]^T,  K = taps * (C1 + C2), fp16 operands, fp32 accumulate.
+// Activations are dense NHWC (common.cuh), GEMM row m = output pixel (s, y, x) in row-major order.  The A tile of a
+// 128-pixel M tile is fetched by the TMA unit itself:
+//   * 3x3 convs: an IM2COL tensor map over [C, W, H, S] (bounding box corners -1/-1, traversal stride = conv stride):
+//     one load per filter tap (r, s) = "128 consecutive output pixels starting at pixel m0, displaced by (s, r)"; the
+//     unit walks across image rows and samples and zero-fills taps that fall outside the image, which is exactly SAME
+//     padding at stride 1 and the explicit pad-1-on-all-sides of the darknet downsample convs (layers.py:616-635).
+//     No padded buffers, no border rows in the GEMM, no im2col matrix.
+//   * 1x1 convs: plain 2D boxes of the [rows, C] matrix; a channel concat [in1, in2] (route, layers.py:583-592) reads
+//     its K range from two maps.
+//   * MC stacking (stack_feature_map, layers.py:595-597) is a 5D im2col map [C, W, H, T, B] whose T stride is ZERO:
+//     sample s = b*T + t of the stacked tensor reads image b of the cached backbone map.  No copy.
 //
 // Structure: persistent CTAs (one per SM), 384 threads = warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
 // allocator, warps 4-11 epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant split the columns); smem ring of `num_stages` {A,B} tiles with
@@ -57,13 +62,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-        "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
 // ---- 2-CTA (cta_group::2) forms: the TMA of either CTA signals the LEADER's barrier (peer bit 24 cleared), the
 // leader's MMA commits are multicast to the barrier at the same offset in both CTAs.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
@@ -71,6 +69,28 @@ __device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"((uint64_t)map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// im2col loads: {c, w, h, n} = first channel and the (input-space) position of the filter's top-left corner for the first
+// output pixel of the tile; {ow, oh} = filter tap.  CG = 2: completion lands on the leader CTA's barrier.
+template <int CG>
+__device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n, int ow, int oh) {
+    if constexpr (CG == 2) {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+            "l"((uint64_t)map), "r"(bar & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)ow), "h"((uint16_t)oh)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+            "l"((uint64_t)map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)ow), "h"((uint16_t)oh)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_im2col_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int d, int n) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %8, %8};" ::"r"(dst),
+        "l"((uint64_t)map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"((uint16_t)0)
         : "memory");
 }
 __device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -288,19 +308,18 @@ __device__ __forceinline__ void chunk_f16(const uint32_t (&raw)[32], const float
 }
 
 __device__ __forceinline__ void stage_and_store(const CUtensorMap* map_o, uint32_t stg, uint32_t stg_row, uint32_t swz, int lane,
-                                                bool valid, const uint4 (&o)[4], int c, int row0) {
+                                                const uint4 (&o)[4], int c, int row0) {
     if (lane == 0) bulk_wait_read0();        // the previous store of this warp has drained the staging block
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const uint32_t dst = stg_row + (((uint32_t)j ^ swz) << 4);
-        const uint4 q = valid ? o[j] : make_uint4(0u, 0u, 0u, 0u);      // border pixels stay zero
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[j].x), "r"(o[j].y), "r"(o[j].z), "r"(o[j].w) : "memory");
     }
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-        tma_store_2d(map_o, stg, c, row0);
+        tma_store_2d(map_o, stg, c, row0);   // rows past the end of the tensor are clipped by the TMA unit
         bulk_commit();
     }
 }
@@ -309,16 +328,16 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map_o, uint32
 template <int CG, int KIND>
 __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const UmmaParams& p, SmemCtl* ctl, uint32_t tmem_base,
                                              uint32_t out_stage, int warp, int lane, uint32_t rank, int first_tile, int tile_step) {
-    constexpr bool kS2 = KIND == EPI_DIRECT;
     constexpr bool kF32 = KIND == EPI_F32;
     constexpr bool kDrop = KIND == EPI_F16_DROP;
     constexpr bool kRes = KIND == EPI_F16_RES;
-    constexpr bool kTma = KIND == EPI_F16 || KIND == EPI_F16_RES || KIND == EPI_F16_DROP || KIND == EPI_F32;
+    constexpr bool kUp = KIND == EPI_UPSAMPLE;
     constexpr int CH = kF32 ? 16 : 32;
     const int quad = warp & 3;
     const int hsel = (warp - 4) >> 2;
     const Epilogue& ep = p.ep;
-    const int Ho = p.gout.H, Wo = p.gout.W, S = p.gout.S;
+    const int Ho = p.gout.H, Wo = p.gout.W;
+    const uint32_t out_rows = (uint32_t)p.out_rows;
     const int nchunks = p.BN / CH;
     const int nnt_shift = p.nnt_shift, BN = p.BN, ldc = ep.ldc;
     const uint32_t stg = out_stage + (uint32_t)(warp - 4) * kStageOutBytes;
@@ -331,32 +350,22 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
         const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
         const int m_tile = (tile >> nnt_shift) * CG + (int)rank;
         const int n0 = (tile & ((1 << nnt_shift) - 1)) * BN;
-        int s, y, x;
-        bool valid;
-        uint32_t row = 0;
-        if constexpr (kS2) {
-            const int tx = m_tile % p.tiles_x, ty = (m_tile / p.tiles_x) % p.tiles_y, bi = m_tile / (p.tiles_x * p.tiles_y);
-            const int bw = i % p.BW, bh = (i / p.BW) % p.BH, bn = i / (p.BW * p.BH);
-            s = bi * p.BI + bn;
-            y = ty * p.BH + bh;
-            x = tx * p.BW + bw;
-            valid = (s < S) && (y < Ho) && (x < Wo);
-        } else {
-            // stride 1: the output has the padded geometry of the input, so the GEMM row IS the padded pixel index
-            row = (uint32_t)m_tile * kTileM + (uint32_t)i;
-            const uint32_t su = fdiv(row, p.fd_plane), rem = row - su * p.fd_plane.d;
-            const uint32_t py = fdiv(rem, p.fd_pw), px = rem - py * p.fd_pw.d;
-            s = (int)su;
-            y = (int)py - 1;
-            x = (int)px - 1;
-            valid = (s < S) && (py >= 1u) && ((int)py <= Ho) && (px >= 1u) && ((int)px <= Wo);
-        }
+        const uint32_t row = (uint32_t)m_tile * kTileM + (uint32_t)i;       // GEMM row == output pixel index
+        const bool valid = row < out_rows;
         DropRow dr{0u, 0u, 0u};
-        if constexpr (kDrop) {
-            const uint32_t im = fdiv((uint32_t)s, p.fd_T);
-            dr.t = (uint32_t)s - im * p.fd_T.d;
-            dr.image = (uint32_t)ep.drop.image0 + im;
-            dr.group0 = ((uint32_t)(y * Wo + x) * (uint32_t)ep.cout + (uint32_t)n0) >> 3;
+        int us = 0, uy = 0, ux = 0;
+        if constexpr (kDrop || kUp) {
+            const uint32_t su = fdiv(row, p.fd_plane), rem = row - su * p.fd_plane.d;        // sample, pixel inside the map
+            if constexpr (kDrop) {
+                const uint32_t im = fdiv(su, p.fd_T);
+                dr.t = su - im * p.fd_T.d;
+                dr.image = (uint32_t)ep.drop.image0 + im;
+                dr.group0 = (rem * (uint32_t)ep.cout + (uint32_t)n0) >> 3;
+            } else {
+                us = (int)su;
+                uy = (int)fdiv(rem, p.fd_w);
+                ux = (int)rem - uy * Wo;
+            }
         }
         const __half* res_row = nullptr;
         uint4 rnext[4] = {};
@@ -402,26 +411,19 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
             } else {
                 chunk_f16<kDrop, kRes>(raw, ctl->bias + c, rcur, o4, ep.drop, dr, (uint32_t)c0 >> 3);
             }
-            if constexpr (kTma) {
-                stage_and_store(map_o, stg, stg_row, swz, lane, valid, o4, c, m_tile * kTileM + quad * 32);
-            } else if (valid) {
+            if constexpr (!kUp) {
+                stage_and_store(map_o, stg, stg_row, swz, lane, o4, c, m_tile * kTileM + quad * 32);
+            } else if (valid) {   // nearest-neighbour x2 -> four destination pixels
                 __half* ob = reinterpret_cast<__half*>(ep.out);
-                if constexpr (kS2) {
-                    const size_t opix = ((size_t)s * (Ho + 2) + (y + 1)) * (Wo + 2) + (x + 1);
-                    uint4* o = reinterpret_cast<uint4*>(ob + opix * ldc + c);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = o4[j];
-                } else {   // EPI_UPSAMPLE: nearest-neighbour x2 -> four destination pixels
+                for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                    for (int dy = 0; dy < 2; ++dy)
+                    for (int dx = 0; dx < 2; ++dx) {
+                        const size_t q = ((size_t)us * (2 * Ho) + (2 * uy + dy)) * (2 * Wo) + (2 * ux + dx);
+                        uint4* o = reinterpret_cast<uint4*>(ob + q * ldc + c);
 #pragma unroll
-                        for (int dx = 0; dx < 2; ++dx) {
-                            const size_t q = ((size_t)s * (2 * Ho + 2) + (2 * y + dy + 1)) * (2 * Wo + 2) + (2 * x + dx + 1);
-                            uint4* o = reinterpret_cast<uint4*>(ob + q * ldc + c);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) o[j] = o4[j];
-                        }
-                }
+                        for (int j = 0; j < 4; ++j) o[j] = o4[j];
+                    }
             }
         }
         tc_fence_before();
@@ -431,14 +433,14 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
             else mbar_arrive_cluster(acc_empty0 + 8 * as, 0);      // the leader's MMA thread waits for both CTAs
         }
     }
-    if (kTma && lane == 0) bulk_wait0();          // all output writes complete before the CTA retires
+    if (!kUp && lane == 0) bulk_wait0();          // all output writes complete before the CTA retires
 }
 
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (cluster of 2) works on 256 rows x BN: each CTA stages its own
 // 128 A rows and HALF of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) for both, every CTA runs
 // the epilogue of its own 128 accumulator rows.  Per SM and MMA cycle this moves 2/3 of the bytes of CG = 1.
-// S2: stride-2 patch mode (the five downsample convs).
-template <int CG, bool S2>
+// AM: how the producer addresses the A operand (AMode in conv_umma.cuh).
+template <int CG, int AM>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o, const UmmaParams p) {
@@ -513,8 +515,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
 
     if (warp == 0) {
         // ================================ TMA producer (whole warp converged, one elected lane issues) ================
-        const int BK = p.BK, BN = p.BN, kbt = p.kb1 + p.kb2, kb1 = p.kb1, in_PW = p.in_PW;
-        const int row_shift0 = (p.taps == 9) ? -in_PW - 1 : 0;
+        const int BK = p.BK, BN = p.BN, kbt = p.kb1 + p.kb2, kb1 = p.kb1, cstride = p.stride;
         const int n_rank = (int)rank * p.b_rows * (CG - 1);                  // CG = 2: my half of B
         const uint32_t a_bytes = p.a_bytes;
         uint32_t stage = 0, phase = 0;
@@ -522,16 +523,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             const int m_tile = (tile >> nnt_shift) * CG + (int)rank;
             const int n0 = (tile & ((1 << nnt_shift) - 1)) * BN + n_rank;
             const int m0 = m_tile * kTileM;
-            int x2 = 0, y2 = 0, b2 = 0;
-            if constexpr (S2) {
-                const int tx = m_tile % p.tiles_x, q = m_tile / p.tiles_x;
-                const int ty = q % p.tiles_y;
-                x2 = 2 * tx * p.BW;
-                y2 = 2 * ty * p.BH;
-                b2 = (q / p.tiles_y) * p.BI;
+            int cw = 0, chh = 0, cn = 0, ct = 0;          // first output pixel of the tile as tensor-map coordinates
+            if constexpr (AM != A_TILED) {
+                const uint32_t q = fdiv((uint32_t)m0, p.fd_w);                // m0 = (n * Ho + ho) * Wo + wo
+                const uint32_t n = fdiv(q, p.fd_h);
+                cw = m0 - (int)(q * p.fd_w.d);
+                chh = (int)(q - n * p.fd_h.d);
+                cn = (int)n;
+                if constexpr (AM == A_IM2COL) {           // top-left corner of the filter window in input space (pad 1)
+                    cw = cw * cstride - 1;
+                    chh = chh * cstride - 1;
+                } else {                                  // stacked source: sample n = b*T + t reads image b
+                    const uint32_t b = fdiv(n, p.fd_T);
+                    ct = (int)(n - b * p.fd_T.d);
+                    cn = (int)b;
+                }
             }
             int cb = 0, r = 0, s = 0;                     // channel block, filter tap (r, s)
-            int a_row = m0 + row_shift0, b_k = 0;
+            int b_k = 0;
             for (int kb = 0; kb < num_kb; kb += kbs) {
                 const int nkb = min(kbs, num_kb - kb);
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -549,19 +558,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                 if (leader_lane && rank == 0) mbar_expect_tx(full, kb_bytes * nkb * CG);   // bytes of both CTAs land on the leader's barrier
                 for (int j = 0; j < nkb; ++j) {
                     if (leader_lane) {
-                        if constexpr (S2) {
-                            tma_load_4d(sa, &map_a1, full, cb * BK, x2 + s, y2 + r, b2);
+                        if constexpr (AM == A_IM2COL) {
+                            tma_im2col_4d<CG>(sa, &map_a1, full, cb * BK, cw, chh, cn, s, r);
+                        } else if constexpr (AM == A_STACK1) {
+                            tma_im2col_5d(sa, &map_a1, full, cb * BK, cw, chh, ct, cn);
+                        } else if constexpr (AM == A_STACK2) {
+                            if (cb < kb1) tma_a2d<CG>(sa, &map_a1, full, cb * BK, m0);
+                            else tma_im2col_5d(sa, &map_a2, full, (cb - kb1) * BK, cw, chh, ct, cn);
                         } else {
-                            if (cb < kb1) tma_a2d<CG>(sa, &map_a1, full, cb * BK, a_row);
-                            else tma_a2d<CG>(sa, &map_a2, full, (cb - kb1) * BK, a_row);
+                            if (cb < kb1) tma_a2d<CG>(sa, &map_a1, full, cb * BK, m0);
+                            else tma_a2d<CG>(sa, &map_a2, full, (cb - kb1) * BK, m0);
                         }
                         tma_a2d<CG>(sa + a_bytes, &map_b, full, b_k, n0);
                     }
                     sa += kb_bytes;
                     b_k += BK;
-                    if (++cb == kbt) {                    // next filter tap: one pixel right, or down a row and two left
+                    if (++cb == kbt) {                    // next filter tap
                         cb = 0;
-                        if (++s == 3) { s = 0; ++r; a_row += in_PW - 2; } else { ++a_row; }
+                        if (++s == 3) { s = 0; ++r; }
                     }
                 }
                 __syncwarp();
@@ -625,25 +639,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), the two warps of a quadrant interleave the column
         // chunks.  A chunk is 64 bytes of output per row (32 fp16 or 16 fp32 columns): TMEM -> registers,
         // [dropout] + shift + leaky [+ residual], convert, then
-        //   * stride-1 layers: the warp's 32 x 64 B block goes to 64B-swizzled shared memory and out with one TMA
-        //     store (rows that are border pixels are written as zeros, which is what the border holds anyway);
-        //   * stride-2 / upsampling layers: 16-byte stores straight from registers (rows are not contiguous there).
+        //   * the warp's 32 x 64 B block goes to 64B-swizzled shared memory and out with one TMA store;
+        //   * the two upsampling layers: 16-byte stores straight from registers (four destination pixels per row).
         // The residual of the next chunk is requested before the current one is processed (the first one before the
         // accumulator barrier), so its latency overlaps TMEM traffic and math.
-        if constexpr (S2) {
-            run_epilogue<CG, EPI_DIRECT>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
-        } else {
-            switch (p.epi_kind) {
-                case EPI_F16: run_epilogue<CG, EPI_F16>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
-                case EPI_F16_RES: run_epilogue<CG, EPI_F16_RES>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
-                case EPI_F16_DROP: run_epilogue<CG, EPI_F16_DROP>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
-                default:
-                    if constexpr (CG == 1) {
-                        if (p.epi_kind == EPI_F32) run_epilogue<CG, EPI_F32>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
-                        else run_epilogue<CG, EPI_UPSAMPLE>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
-                    }
-                    break;
-            }
+        switch (p.epi_kind) {
+            case EPI_F16: run_epilogue<CG, EPI_F16>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+            case EPI_F16_RES: run_epilogue<CG, EPI_F16_RES>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+            case EPI_F16_DROP: run_epilogue<CG, EPI_F16_DROP>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+            default:
+                if constexpr (CG == 1 && AM == A_TILED) {
+                    if (p.epi_kind == EPI_F32) run_epilogue<CG, EPI_F32>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
+                    else run_epilogue<CG, EPI_UPSAMPLE>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
+                }
+                break;
         }
     }
 
@@ -669,17 +678,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static void* driver_fn(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) return p;
+    return nullptr;
+}
 static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    });
+    static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_fn("cuTensorMapEncodeTiled"));
+    return fn;
+}
+static EncodeIm2colFn encode_im2col_fn() {
+    static EncodeIm2colFn fn = reinterpret_cast<EncodeIm2colFn>(driver_fn("cuTensorMapEncodeIm2col"));
     return fn;
 }
 
@@ -702,6 +716,30 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
     return 0;
 }
 
+// im2col map over a dense fp16 NHWC tensor.  rank 4: dims {C, W, H, S}, corner = -pad / -pad (3x3, pad 1) or 0 / 0.
+// rank 5: dims {C, W, H, T, B} with a ZERO byte stride on T (MC stacking), 1x1 only.  Semantics verified on the device with
+// tools/micro/im2col_probe.cu: the unit walks `pixels` consecutive filter-window positions (W fastest, then H, then the
+// outer dims), `tstride` apart, adds the per-instruction tap offset, and zero-fills whatever falls outside the tensor.
+static int make_im2col_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, int corner,
+                           int tstride, int channels, int pixels, int swizzle_bytes) {
+    EncodeIm2colFn fn = encode_im2col_fn();
+    BY_REQUIRE(fn != nullptr, "cuTensorMapEncodeIm2col not available from the driver");
+    cuuint64_t d[5], s[4];
+    cuuint32_t e[5] = {1, (cuuint32_t)tstride, (cuuint32_t)tstride, 1, 1};
+    int lo[3] = {corner, corner, 0}, up[3] = {corner, corner, 0};
+    for (int i = 0; i < rank; ++i) d[i] = dims[i];
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, lo, up, (cuuint32_t)channels,
+                    (cuuint32_t)pixels, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeIm2col failed with CUresult " + std::to_string((int)r));
+        return -3;
+    }
+    return 0;
+}
+
 static FastDiv make_fastdiv(uint32_t d) {
     FastDiv f{d, 0u, 0u};
     if (d <= 1) { f.d = 1; return f; }
@@ -713,29 +751,21 @@ static FastDiv make_fastdiv(uint32_t d) {
     return f;
 }
 
-// best (BW, BH, BI) with BW*BH*BI == 128 for a stride-2 output of S x Ho x Wo
-static void pick_patch(int S, int Ho, int Wo, int* BW, int* BH, int* BI) {
-    double best = -1;
-    for (int bw = 1; bw <= 128; bw *= 2)
-        for (int bh = 1; bw * bh <= 128; bh *= 2) {
-            const int bi = 128 / (bw * bh);
-            auto cdiv = [](int a, int b) { return (a + b - 1) / b; };
-            const double eff = (double)S * Ho * Wo / ((double)cdiv(S, bi) * bi * cdiv(Ho, bh) * bh * cdiv(Wo, bw) * bw);
-            // prefer wider rows on ties (longer contiguous TMA segments)
-            if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > *BW)) { best = eff; *BW = bw; *BH = bh; *BI = bi; }
-        }
-}
-
 int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     std::memset(L, 0, sizeof(*L));
     UmmaParams& p = L->p;
     const Geom& g = q.gin;
     const int C1 = g.C, C2 = q.in2 ? q.c2 : 0;
+    const int t1 = std::max(q.t1, 1), t2 = std::max(q.t2, 1);
     BY_REQUIRE(q.k == 1 || q.k == 3, "kernel size must be 1 or 3 (layers.py:528)");
     BY_REQUIRE(q.stride == 1 || (q.stride == 2 && q.k == 3 && !q.in2), "stride 2 only as the 3x3 downsample conv");
     BY_REQUIRE(!(q.in2 && q.k != 1), "channel-concat input only for 1x1 convs");
     BY_REQUIRE(C1 % 32 == 0 && C2 % 32 == 0, "channel counts must be multiples of 32");
     BY_REQUIRE(q.cout_pad % 16 == 0 && q.cout_pad <= kMaxBias, "padded cout must be a multiple of 16 and <= 1024");
+    BY_REQUIRE(g.H % q.stride == 0 && g.W % q.stride == 0, "stride-2 convs need even maps");
+    BY_REQUIRE((t1 == 1 && t2 == 1) || q.k == 1, "MC-stacked sources only feed 1x1 convs");
+    BY_REQUIRE(!(t1 > 1 && q.in2) && !(t2 > 1 && !q.in2), "stacked source: in1 alone, or in2 of a concat");
+    BY_REQUIRE(g.S % t1 == 0 && g.S % t2 == 0, "sample count must be a multiple of the stacking factor");
     p.BK = (C1 % 64 == 0 && C2 % 64 == 0) ? 64 : 32;
     p.taps = q.k * q.k;
     p.kb1 = C1 / p.BK;
@@ -745,35 +775,40 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.num_n_tiles = q.cout_pad / p.BN;
     BY_REQUIRE((p.num_n_tiles & (p.num_n_tiles - 1)) == 0, "the number of N tiles must be a power of two");
     for (p.nnt_shift = 0; (1 << p.nnt_shift) < p.num_n_tiles; ++p.nnt_shift) {}
+    p.amode = q.k == 3 ? A_IM2COL : (t1 > 1 ? A_STACK1 : (t2 > 1 ? A_STACK2 : A_TILED));
+    p.stride = q.stride;
     // CTA pairs for the feed-bound shapes: 3x3 stride-1 convs with wide N tiles
     static const int cg_env = getenv("BYOLO_CG") ? atoi(getenv("BYOLO_CG")) : 0;     // 1 = force off, 2 = default policy
     p.cg = (cg_env != 1 && q.k == 3 && q.stride == 1 && p.BN >= 128 && p.BK == 64) ? 2 : 1;
     p.b_rows = p.BN / p.cg;
     static const int dbg_env = getenv("BYOLO_DBG") ? atoi(getenv("BYOLO_DBG")) : 0;
     p.dbg = dbg_env;
-    p.in_PW = g.PW();
-    p.s2 = q.stride == 2;
     p.gout.S = g.S;
     p.gout.H = g.H / q.stride;
     p.gout.W = g.W / q.stride;
     p.gout.C = q.ep.cout;
-    if (q.ep.out_mode != OUT_PADDED_F32) BY_REQUIRE(q.ep.cout % 32 == 0 && q.ep.ldc % 32 == 0, "fp16 outputs need cout % 32 == 0");
-    else BY_REQUIRE(q.ep.ldc == q.cout_pad && !p.s2, "fp32 (detection) outputs are stored cout_pad wide, stride 1 only");
+    p.out_rows = (long long)p.gout.S * p.gout.H * p.gout.W;
+    BY_REQUIRE(p.out_rows < (1ll << 31) && g.rows() < (1ll << 31), "activation map too large for 32-bit row indices");
+    if (q.ep.out_mode != OUT_DENSE_F32) BY_REQUIRE(q.ep.cout % 32 == 0 && q.ep.ldc % 32 == 0, "fp16 outputs need cout % 32 == 0");
+    else BY_REQUIRE(q.ep.ldc == q.cout_pad && q.stride == 1, "fp32 (detection) outputs are stored cout_pad wide, stride 1 only");
     p.ep = q.ep;
     p.ep.drop.thr16 = std::min<uint32_t>(p.ep.drop.thr16, 65535u);
-    if (p.s2) p.epi_kind = EPI_DIRECT;
-    else if (q.ep.out_mode == OUT_PADDED_F32) p.epi_kind = EPI_F32;
+    if (q.ep.out_mode == OUT_DENSE_F32) p.epi_kind = EPI_F32;
     else if (q.ep.out_mode == OUT_UPSAMPLE2) p.epi_kind = EPI_UPSAMPLE;
     else if (q.ep.drop.enabled) p.epi_kind = EPI_F16_DROP;
     else if (q.ep.residual) p.epi_kind = EPI_F16_RES;
     else p.epi_kind = EPI_F16;
     BY_REQUIRE((p.epi_kind == EPI_F32) == !q.ep.leaky, "fp16 outputs are conv+BN+leaky layers, the fp32 output is the linear detection conv");
-    BY_REQUIRE(!(q.ep.drop.enabled && (q.ep.residual || p.epi_kind != EPI_F16_DROP)), "dropout only on plain stride-1 convs");
-    BY_REQUIRE(!(q.ep.residual && p.epi_kind != EPI_F16_RES), "residual only on plain stride-1 convs");
-    BY_REQUIRE(g.rows() < (1ll << 31), "activation map too large for 32-bit row indices");
-    p.fd_plane = make_fastdiv((uint32_t)(g.PH() * g.PW()));
-    p.fd_pw = make_fastdiv((uint32_t)g.PW());
-    p.fd_T = make_fastdiv((uint32_t)std::max(q.ep.drop.T, 1));
+    BY_REQUIRE(!(q.ep.drop.enabled && (q.ep.residual || p.epi_kind != EPI_F16_DROP)), "dropout only on plain convs");
+    BY_REQUIRE(!(q.ep.residual && p.epi_kind != EPI_F16_RES), "residual only on plain convs");
+    BY_REQUIRE(!((p.epi_kind == EPI_F32 || p.epi_kind == EPI_UPSAMPLE) && p.amode != A_TILED), "detection / upsampling convs are plain 1x1 convs");
+    p.fd_plane = make_fastdiv((uint32_t)(p.gout.H * p.gout.W));
+    p.fd_w = make_fastdiv((uint32_t)p.gout.W);
+    p.fd_h = make_fastdiv((uint32_t)p.gout.H);
+    // A_STACK*: sample -> (image, t) of the stacked source; dropout: sample -> (image, t) of the mask stream (same T)
+    const int Tdiv = p.amode == A_STACK1 ? t1 : (p.amode == A_STACK2 ? t2 : std::max(q.ep.drop.T, 1));
+    BY_REQUIRE(!(q.ep.drop.enabled && p.amode >= A_STACK1 && Tdiv != q.ep.drop.T), "stacking factor and dropout T differ");
+    p.fd_T = make_fastdiv((uint32_t)Tdiv);
     const int swz = p.BK * 2;                                     // 128B or 64B rows
     p.sbo_bytes = 8 * swz;
     p.layout_type = (swz == 128) ? 2u : 4u;                       // SWIZZLE_128B / SWIZZLE_64B
@@ -790,29 +825,28 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     L->smem_bytes = p.num_stages * stage_bytes + 1024 + sizeof(SmemCtl) + kEpiWarps * kStageOutBytes + 64;
 
     const uint32_t one[5] = {1, 1, 1, 1, 1};
-    if (!p.s2) {
-        const long long rows = g.rows();
-        p.num_m_tiles = (int)((rows + kTileM - 1) / kTileM);
-        uint64_t d1[2] = {(uint64_t)C1, (uint64_t)rows}, s1[1] = {(uint64_t)C1 * 2};
-        uint32_t box[2] = {(uint32_t)p.BK, (uint32_t)kTileM};
-        if (int e = make_map(&L->a1, q.in1, 2, d1, s1, box, one, swz)) return e;
-        if (q.in2) {
-            uint64_t d2[2] = {(uint64_t)C2, (uint64_t)rows}, s2[1] = {(uint64_t)C2 * 2};
-            if (int e = make_map(&L->a2, q.in2, 2, d2, s2, box, one, swz)) return e;
-        } else {
-            L->a2 = L->a1;
-        }
-    } else {
-        pick_patch(p.gout.S, p.gout.H, p.gout.W, &p.BW, &p.BH, &p.BI);
-        p.tiles_x = (p.gout.W + p.BW - 1) / p.BW;
-        p.tiles_y = (p.gout.H + p.BH - 1) / p.BH;
-        p.num_m_tiles = p.tiles_x * p.tiles_y * ((p.gout.S + p.BI - 1) / p.BI);
-        uint64_t d[4] = {(uint64_t)C1, (uint64_t)g.PW(), (uint64_t)g.PH(), (uint64_t)g.S};
-        uint64_t s[3] = {(uint64_t)C1 * 2, (uint64_t)C1 * 2 * g.PW(), (uint64_t)C1 * 2 * g.PW() * g.PH()};
-        uint32_t box[4] = {(uint32_t)p.BK, (uint32_t)(2 * p.BW), (uint32_t)(2 * p.BH), (uint32_t)p.BI};
-        uint32_t es[4] = {1, 2, 2, 1};
-        if (int e = make_map(&L->a1, q.in1, 4, d, s, box, es, swz)) return e;
+    p.num_m_tiles = (int)((p.out_rows + kTileM - 1) / kTileM);
+    const uint32_t box_a[2] = {(uint32_t)p.BK, (uint32_t)kTileM};
+    if (p.amode == A_IM2COL) {
+        const uint64_t d[4] = {(uint64_t)C1, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.S};
+        const uint64_t st[3] = {(uint64_t)C1 * 2, (uint64_t)C1 * 2 * g.W, (uint64_t)C1 * 2 * g.W * g.H};
+        if (int e = make_im2col_map(&L->a1, q.in1, 4, d, st, -1, q.stride, p.BK, kTileM, swz)) return e;
         L->a2 = L->a1;
+    } else {
+        auto stacked = [&](CUtensorMap* m, const void* base, int C, int T) {
+            const uint64_t d[5] = {(uint64_t)C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)T, (uint64_t)(g.S / T)};
+            const uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)C * 2 * g.W, 0ull, (uint64_t)C * 2 * g.W * g.H};
+            return make_im2col_map(m, base, 5, d, st, 0, 1, p.BK, kTileM, swz);
+        };
+        auto tiled = [&](CUtensorMap* m, const void* base, int C) {
+            const uint64_t d[2] = {(uint64_t)C, (uint64_t)g.rows()}, st[1] = {(uint64_t)C * 2};
+            return make_map(m, base, 2, d, st, box_a, one, swz);
+        };
+        if (p.amode == A_STACK1) { if (int e = stacked(&L->a1, q.in1, C1, t1)) return e; }
+        else if (int e = tiled(&L->a1, q.in1, C1)) return e;
+        if (!q.in2) L->a2 = L->a1;
+        else if (p.amode == A_STACK2) { if (int e = stacked(&L->a2, q.in2, C2, t2)) return e; }
+        else if (int e = tiled(&L->a2, q.in2, C2)) return e;
     }
     {
         const uint64_t K = (uint64_t)p.taps * (C1 + C2);
@@ -821,11 +855,10 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
         if (int e = make_map(&L->b, q.w16, 2, d, s, box, one, swz)) return e;
     }
     L->o = L->b;
-    if (!p.s2 && q.ep.out_mode != OUT_UPSAMPLE2) {
-        // output map: [rows, ldc] of the padded output buffer (same row indexing as the A operand), 32 x 64 B boxes
-        const bool f32 = q.ep.out_mode == OUT_PADDED_F32;
-        const long long rows = g.rows();
-        uint64_t d[2] = {(uint64_t)q.ep.ldc, (uint64_t)rows}, st[1] = {(uint64_t)q.ep.ldc * (f32 ? 4 : 2)};
+    if (p.epi_kind != EPI_UPSAMPLE) {
+        // output map: [rows, ldc] of the dense output, 32 x 64 B boxes
+        const bool f32 = p.epi_kind == EPI_F32;
+        uint64_t d[2] = {(uint64_t)q.ep.ldc, (uint64_t)p.out_rows}, st[1] = {(uint64_t)q.ep.ldc * (f32 ? 4 : 2)};
         uint32_t box[2] = {(uint32_t)(f32 ? 16 : 32), 32u};
         if (int e = make_map(&L->o, q.ep.out, 2, d, st, box, one, 64, f32)) return e;
     }
@@ -837,11 +870,14 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_umma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(conv_umma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(conv_umma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        auto set = [](const void* f) {
+            if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        };
+        set((const void*)conv_umma_kernel<1, A_TILED>);
+        set((const void*)conv_umma_kernel<1, A_IM2COL>);
+        set((const void*)conv_umma_kernel<1, A_STACK1>);
+        set((const void*)conv_umma_kernel<1, A_STACK2>);
+        set((const void*)conv_umma_kernel<2, A_IM2COL>);
     });
     BY_CUDA(attr_err);
     return 0;
@@ -864,11 +900,16 @@ int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
         attr[1].val.clusterDim.y = 1;
         attr[1].val.clusterDim.z = 1;
         cfg.numAttrs = 2;
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, false>, L.a1, L.a2, L.b, L.o, L.p));
-    } else if (L.p.s2) {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, true>, L.a1, L.a2, L.b, L.o, L.p));
+        BY_REQUIRE(L.p.amode == A_IM2COL, "CTA pairs are only used for 3x3 convs");
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_IM2COL>, L.a1, L.a2, L.b, L.o, L.p));
+    } else if (L.p.amode == A_IM2COL) {
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL>, L.a1, L.a2, L.b, L.o, L.p));
+    } else if (L.p.amode == A_STACK1) {
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1>, L.a1, L.a2, L.b, L.o, L.p));
+    } else if (L.p.amode == A_STACK2) {
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2>, L.a1, L.a2, L.b, L.o, L.p));
     } else {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, false>, L.a1, L.a2, L.b, L.o, L.p));
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED>, L.a1, L.a2, L.b, L.o, L.p));
     }
     return 0;
 }

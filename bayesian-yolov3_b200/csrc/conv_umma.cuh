@@ -6,12 +6,19 @@ namespace byolo {
 
 // epilogue specialisations of conv_umma_kernel (run_epilogue<KIND>)
 enum EpiKind : int {
-    EPI_F16 = 0,        // shift + leaky -> fp16, TMA store (stride-1 convs)
+    EPI_F16 = 0,        // shift + leaky -> fp16, TMA store
     EPI_F16_RES = 1,    //   ... + residual shortcut (layers.py:505-507)
     EPI_F16_DROP = 2,   //   dropout before the shift (layers.py:521-524, 560-570)
     EPI_F32 = 3,        // + bias, linear -> fp32 raw detection map, TMA store (layers.py:600-613)
-    EPI_DIRECT = 4,     // stride-2 patch tiles: shift + leaky -> fp16, 16-byte stores
-    EPI_UPSAMPLE = 5,   // shift + leaky -> fp16 stored to the four pixels of the nearest x2 upsample (layers.py:578-580)
+    EPI_UPSAMPLE = 4,   // shift + leaky -> fp16 stored to the four pixels of the nearest x2 upsample (layers.py:578-580)
+};
+
+// how the TMA producer fetches the A operand (activations)
+enum AMode : int {
+    A_TILED = 0,        // 1x1 conv: plain 2D boxes of the [rows, C] matrix (in1, then in2 for a channel concat)
+    A_IM2COL = 1,       // 3x3 conv, stride 1 or 2: 4D im2col map over [C, W, H, S], one load per filter tap, padding = OOB zero fill
+    A_STACK1 = 2,       // 1x1 conv whose in1 is an MC-stacked map (layers.py:595-597): 5D im2col map [C, W, H, T, B], T stride 0
+    A_STACK2 = 3,       // 1x1 conv over [in1 (2D boxes), in2 = MC-stacked map (5D, T stride 0)]
 };
 
 // n / d for n < 2^31 as umulhi(n, mul) >> shr (d == 1: identity)
@@ -28,16 +35,16 @@ struct UmmaParams {
     int a_bytes, b_bytes;          // bytes of one A / B stage tile
     int taps;                      // 1 | 9
     int kb1, kb2;                  // K blocks per tap read from in1 / in2
-    int in_PW;                     // padded width of the input (row shift of one filter row)
-    int s2;                        // stride-2 patch mode
-    int BW, BH, BI, tiles_x, tiles_y;
-    Geom gout;                     // un-padded output geometry
+    int amode;                     // AMode
+    int stride;                    // 1 | 2 (3x3 only)
+    Geom gout;                     // output geometry (S samples x H x W, C = valid output channels)
+    long long out_rows;            // S*H*W of the output
     Epilogue ep;
     uint32_t idesc;                // tcgen05 instruction descriptor
     uint32_t sbo_bytes, layout_type;
     int epi_kind;                  // EpiKind
     int nnt_shift;                 // log2(num_n_tiles)
-    FastDiv fd_plane, fd_pw, fd_T; // stride-1 row -> (sample, padded y, padded x); sample -> (image, MC sample t)
+    FastDiv fd_plane, fd_w, fd_h, fd_T;   // output row -> (sample, y, x); sample -> (image, MC sample t)
     int dbg;                       // experiments only (-DBYOLO_DBG_HOOKS, BYOLO_DBG): 1 = no operand TMA loads, 2 = no epilogue work, 4 = no MMAs
     unsigned long long* clk;       // profiling: {clock64, globaltimer} at start and end of CTA 0 (effective SM clock), or null
 };

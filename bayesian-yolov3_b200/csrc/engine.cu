@@ -95,13 +95,13 @@ static int fold_and_upload(const LayerDef& d, const float* kernel, const float* 
 
 struct Buffer {
     void* ptr = nullptr;
-    Geom g{0, 0, 0, 0};            // padded-NHWC geometry; C = stored channels
+    Geom g{0, 0, 0, 0};            // dense NHWC geometry; C = stored channels
     bool f32 = false;              // raw detection maps are fp32 (C = cout padded to 16), everything else is T
     int valid_c = 0;               // channels that carry data (== C except for the raw detection maps)
     size_t bytes = 0;
 };
 
-enum StepKind { STEP_STEM, STEP_CONV, STEP_STACK };
+enum StepKind { STEP_STEM, STEP_CONV };
 
 struct Step {
     StepKind kind;
@@ -109,10 +109,6 @@ struct Step {
     ConvProblem prob{};
     UmmaLaunch ul{};
     int out_buf = -1;
-    // stack
-    const void* src = nullptr;
-    void* dst = nullptr;
-    long long plane_bytes = 0;
 };
 
 struct Plan {
@@ -186,21 +182,25 @@ static int new_buffer(byolo_engine* e, Plan* pl, int S, int H, int W, int C, boo
     b.valid_c = C;
     b.bytes = (size_t)b.g.rows() * C * (f32 ? 4 : e->esize());
     BY_CUDA(cudaMalloc(&b.ptr, b.bytes));
-    BY_CUDA(cudaMemset(b.ptr, 0, b.bytes));      // padded buffers: the border is written exactly once, here
+    BY_CUDA(cudaMemset(b.ptr, 0, b.bytes));
     pl->bufs.push_back(b);
     *id = (int)pl->bufs.size() - 1;
     return 0;
 }
 
-// Appends the conv step of layer `li`.  in2 < 0: single input.  residual < 0: none.
-static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int residual, int out_mode, int drop_id, int* out_id) {
+// Appends the conv step of layer `li`.  in2 < 0: single input.  residual < 0: none.  t1 / t2 > 1: that input is a cached
+// backbone map of B images which the conv reads as B*T stacked samples (stack_feature_map, layers.py:595-597).
+static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int residual, int out_mode, int drop_id, int* out_id,
+                    int t1 = 1, int t2 = 1) {
     const LayerDef& d = e->layers[li];
     const LayerWeights& w = e->weights[li];
-    const Buffer bin = pl->bufs[in1];
+    Buffer bin = pl->bufs[in1];
+    bin.g.S *= t1;                                  // geometry as the conv sees it
     BY_REQUIRE(bin.g.C + (in2 >= 0 ? pl->bufs[in2].g.C : 0) == d.cin, "plan wiring: channel mismatch");
+    BY_REQUIRE(in2 < 0 || pl->bufs[in2].g.S * t2 == bin.g.S, "plan wiring: sample count mismatch");
     const int Ho = bin.g.H / d.s, Wo = bin.g.W / d.s;
     int ob;
-    if (out_mode == OUT_PADDED_F32) {
+    if (out_mode == OUT_DENSE_F32) {
         if (int r = new_buffer(e, pl, bin.g.S, Ho, Wo, w.cout_pad, true, &ob)) return r;
         pl->bufs[ob].valid_c = d.cout;
     } else if (out_mode == OUT_UPSAMPLE2) {
@@ -217,6 +217,8 @@ static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int res
     p.in2 = in2 >= 0 ? pl->bufs[in2].ptr : nullptr;
     p.gin = bin.g;
     p.c2 = in2 >= 0 ? pl->bufs[in2].g.C : 0;
+    p.t1 = t1;
+    p.t2 = t2;
     p.k = d.k;
     p.stride = d.s;
     p.cout_pad = w.cout_pad;
@@ -226,7 +228,7 @@ static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int res
     p.ep.residual = residual >= 0 ? pl->bufs[residual].ptr : nullptr;
     p.ep.out = pl->bufs[ob].ptr;
     p.ep.out_mode = out_mode;
-    p.ep.ldc = out_mode == OUT_PADDED_F32 ? w.cout_pad : d.cout;
+    p.ep.ldc = out_mode == OUT_DENSE_F32 ? w.cout_pad : d.cout;
     p.ep.cout = d.cout;
     p.ep.leaky = d.bn;
     p.ep.drop.enabled = drop_id >= 0;
@@ -238,21 +240,6 @@ static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int res
         if (int r = umma_prepare(p, &st.ul)) return r;
     pl->steps.push_back(st);
     pl->conv_out[li] = ob;
-    *out_id = ob;
-    return 0;
-}
-
-static int add_stack(byolo_engine* e, Plan* pl, int src, int B, int T, int* out_id) {
-    if (T == 1) { *out_id = src; return 0; }
-    const Buffer bs = pl->bufs[src];
-    int ob;
-    if (int r = new_buffer(e, pl, B * T, bs.g.H, bs.g.W, bs.g.C, false, &ob)) return r;
-    Step st;
-    st.kind = STEP_STACK;
-    st.src = bs.ptr;
-    st.dst = pl->bufs[ob].ptr;
-    st.plane_bytes = (long long)bs.g.PH() * bs.g.PW() * bs.g.C * e->esize();
-    pl->steps.push_back(st);
     *out_id = ob;
     return 0;
 }
@@ -277,10 +264,10 @@ static int build_plan(byolo_engine* e, int B, Plan* pl) {
     const int blocks[5] = {1, 2, 8, 8, 4};
     int taps[5];
     for (int sidx = 0; sidx < 5; ++sidx) {
-        if (int r = add_conv(e, pl, li++, cur, -1, -1, OUT_PADDED, -1, &cur)) return r;            // downsample
+        if (int r = add_conv(e, pl, li++, cur, -1, -1, OUT_DENSE, -1, &cur)) return r;            // downsample
         for (int b = 0; b < blocks[sidx]; ++b) {                                                   // residual block
-            if (int r = add_conv(e, pl, li++, cur, -1, -1, OUT_PADDED, -1, &tmp)) return r;
-            if (int r = add_conv(e, pl, li++, tmp, -1, cur, OUT_PADDED, -1, &cur)) return r;       // + shortcut (model.py:96-99)
+            if (int r = add_conv(e, pl, li++, cur, -1, -1, OUT_DENSE, -1, &tmp)) return r;
+            if (int r = add_conv(e, pl, li++, tmp, -1, cur, OUT_DENSE, -1, &cur)) return r;       // + shortcut (model.py:96-99)
         }
         taps[sidx] = cur;
     }
@@ -293,20 +280,24 @@ static int build_plan(byolo_engine* e, int B, Plan* pl) {
     int route_src = -1;
     const int srcs[3] = {l74, l61, l36};
     for (int j = 0; j < 3; ++j) {
-        int x1, x2 = -1;
-        if (j == 0) {
-            if (int r = add_stack(e, pl, srcs[0], B, T, &x1)) return r;                            // stack_feature_map(-1, T)
-        } else {
+        // stack_feature_map(-1 | 61 | 36, T) is not materialised: the first conv of each head reads the cached backbone
+        // map of B images as B*T samples (t1 / t2 = T)
+        int x1 = srcs[0], x2 = -1;
+        if (j > 0) {
             if (int r = add_conv(e, pl, li++, route_src, -1, -1, OUT_UPSAMPLE2, -1, &x1)) return r;  // conv 84/96 + upsample
-            if (int r = add_stack(e, pl, srcs[j], B, T, &x2)) return r;                            // stack_feature_map(61|36, T)
+            x2 = srcs[j];
         }
         int x = x1, c5 = -1;
         for (int i = 0; i < 6; ++i) {
             const int l = li++;
-            if (int r = add_conv(e, pl, l, x, (i == 0) ? x2 : -1, -1, OUT_PADDED, drop_id(l), &x)) return r;
+            if (i == 0) {
+                if (int r = add_conv(e, pl, l, x, x2, -1, OUT_DENSE, drop_id(l), &x, j == 0 ? T : 1, j == 0 ? 1 : T)) return r;
+            } else if (int r = add_conv(e, pl, l, x, -1, -1, OUT_DENSE, drop_id(l), &x)) {
+                return r;
+            }
             if (i == 4) c5 = x;
         }
-        if (int r = add_conv(e, pl, li++, x, -1, -1, OUT_PADDED_F32, -1, &pl->raw_buf[j])) return r;  // detection conv
+        if (int r = add_conv(e, pl, li++, x, -1, -1, OUT_DENSE_F32, -1, &pl->raw_buf[j])) return r;  // detection conv
         route_src = c5;                                                                            // route([-3])
     }
     BY_REQUIRE(li == (int)e->layers.size(), "plan did not consume all layers");
@@ -347,8 +338,6 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
             } else if (int r = launch_stem(img, pl->B, c.height, c.width, w.w32, w.bias, pl->bufs[s.out_buf].ptr, e->act_half(), st)) {
                 return r;
             }
-        } else if (s.kind == STEP_STACK) {
-            if (int r = launch_stack(s.src, s.dst, s.plane_bytes, pl->B, c.T, st)) return r;
         } else {
             if (c.precision == BYOLO_PREC_FP16) {
                 Dropout& d = s.ul.p.ep.drop;
@@ -372,7 +361,7 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
         dp.raw[j] = (const float*)pl->bufs[pl->raw_buf[j]].ptr;
         dp.ld[j] = pl->bufs[pl->raw_buf[j]].g.C;
     }
-    dp.padded = 1;
+    dp.padded = 0;
     for (int i = 0; i < 9; ++i) { dp.prior_h[i] = c.prior_h[i]; dp.prior_w[i] = c.prior_w[i]; }
     dp.rows = rows;
     dp.N = e->N;
@@ -526,12 +515,10 @@ int byolo_profile_read(byolo_handle h, float* ms, int32_t* kind, int32_t* layer,
             const Step& s = pl->steps[i];
             kind[i] = (int)s.kind;
             layer[i] = s.layer;
-            if (s.kind != STEP_STACK) {
-                const LayerDef& d = h->layers[s.layer];
-                const Buffer& ob = pl->bufs[s.out_buf];
-                const int up = (s.kind == STEP_CONV && s.prob.ep.out_mode == OUT_UPSAMPLE2) ? 4 : 1;
-                flops[i] = 2.0 * d.k * d.k * d.cin * d.cout * (double)ob.g.S * ob.g.H * ob.g.W / up;
-            }
+            const LayerDef& d = h->layers[s.layer];
+            const Buffer& ob = pl->bufs[s.out_buf];
+            const int up = (s.kind == STEP_CONV && s.prob.ep.out_mode == OUT_UPSAMPLE2) ? 4 : 1;
+            flops[i] = 2.0 * d.k * d.k * d.cin * d.cout * (double)ob.g.S * ob.g.H * ob.g.W / up;
         } else {
             kind[i] = 3 + (i - (int)pl->steps.size());      // 3 decode, 4 nms
             layer[i] = -1;
@@ -658,7 +645,7 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
     const int Ho = H / stride, Wo = W / stride;
     const bool dense = bn_host == nullptr;
     const Geom go{S, upsample ? 2 * Ho : Ho, upsample ? 2 * Wo : Wo, dense ? w.cout_pad : cout};
-    float* tmp = nullptr;          // dense path: un-padded but still cout_pad wide
+    float* tmp = nullptr;          // detection conv: output is cout_pad wide
     auto alloc0 = [&](void** p, size_t bytes) {
         if (rc) return;
         if (cudaMalloc(p, bytes) != cudaSuccess || cudaMemsetAsync(*p, 0, bytes, st) != cudaSuccess) {
@@ -689,7 +676,7 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
         p.in1 = p1; p.in2 = p2; p.gin = g1; p.c2 = cin2; p.k = k; p.stride = stride;
         p.cout_pad = w.cout_pad; p.w16 = w.w16; p.w32 = w.w32;
         p.ep.bias = w.bias; p.ep.residual = pr; p.ep.out = po;
-        p.ep.out_mode = dense ? OUT_PADDED_F32 : (upsample ? OUT_UPSAMPLE2 : OUT_PADDED);
+        p.ep.out_mode = dense ? OUT_DENSE_F32 : (upsample ? OUT_UPSAMPLE2 : OUT_DENSE);
         p.ep.ldc = go.C; p.ep.cout = cout; p.ep.leaky = d.bn;
         p.ep.drop.enabled = dropout_layer >= 0;
         p.ep.drop.layer_id = dropout_layer; p.ep.drop.T = T > 0 ? T : 1; p.ep.drop.image0 = image_index0;
@@ -730,7 +717,7 @@ int byolo_get_activation(byolo_handle h, int32_t conv_index, float* dst_dev, siz
     BY_REQUIRE(capacity >= n, "destination too small");
     cudaStream_t st = (cudaStream_t)stream;
     if (!b.f32) return launch_unpack(b.ptr, dst_dev, b.g, h->act_half(), st);
-    // raw detection map: fp32, stored cout_pad wide -> un-pad, then drop the padding channels
+    // raw detection map: fp32, stored cout_pad wide -> drop the padding channels
     float* tmp = nullptr;
     const size_t pix = (size_t)b.g.S * b.g.H * b.g.W;
     BY_CUDA(cudaMalloc(&tmp, pix * b.g.C * 4));

@@ -1,5 +1,5 @@
 // K1b (product path): stem conv 3 -> 32, 3x3 stride 1 SAME + BN shift + leaky (darknet.py:10 -> layers.py:545-575),
-// reading the fp32 image [B,H,W,3] in [0,1) (dataset_utils.py:6-11) and writing the padded-NHWC fp16 map.
+// reading the fp32 image [B,H,W,3] in [0,1) (dataset_utils.py:6-11) and writing the dense NHWC fp16 map.
 //
 // K = 27 is far too shallow for a tcgen05 pipeline (one 128x32x32 tile per 128 pixels, nothing to overlap), and the
 // layer is bound by its 64 B/pixel output, so the contraction runs on warp-level mma.sync m16n8k16 (fp16 operands,
@@ -116,8 +116,8 @@ stem_mma_kernel(const float* __restrict__ img, int H, int W, int num_tiles, cons
             *reinterpret_cast<__half2*>(so + (g + 8) * kOutPitch + nt * 8 + 2 * t) = __floats2half2_rn(v2, v3);
         }
         __syncwarp();
-        // 16 pixels x 64 B, contiguous in the padded output row
-        __half* o = out + (((long long)b * (H + 2) + (y0 + ly) + 1) * (W + 2) + (x0 + lx) + 1) * 32;
+        // 16 pixels x 64 B, contiguous in the output row
+        __half* o = out + (((long long)b * H + (y0 + ly)) * W + (x0 + lx)) * 32;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int idx = lane + 32 * j, row = idx >> 2, q = idx & 3;

@@ -245,7 +245,7 @@ def main():
                             'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                             'peak_source': peak_src, 'traffic': traffic, 'conv_share_of_step': conv_ms / step_ms if step_ms else None,
                             'flops_per_image': eng.flops_per_image(), 'step_tflops': eng.flops_per_image() * B / (ms / K * 1e-3) / 1e12},
-               'breakdown_ms': {k: sum(p['ms'] for p in prof if p['kind'] == k) for k in ('stem', 'conv', 'stack', 'decode', 'nms')}}
+               'breakdown_ms': {k: sum(p['ms'] for p in prof if p['kind'] == k) for k in ('stem', 'conv', 'decode', 'nms')}}
         big = [p for p in conv if p['ms'] > 0.3 and p['sm_mhz'] > 0]
         if big:      # effective SM clock inside the long conv launches (clock64/globaltimer): shows power-cap throttling
             res['clocks']['sm_mhz_in_conv_kernels'] = sum(p['sm_mhz'] * p['ms'] for p in big) / sum(p['ms'] for p in big)

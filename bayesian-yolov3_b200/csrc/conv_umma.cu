@@ -228,8 +228,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
     return d;
 }
 
-constexpr int kThreads = 384;          // 4 control warps + 8 epilogue warps
-constexpr int kEpiWarps = 8;
+constexpr int kCtlWarps = 4;            // TMA producer (A), MMA issuer, TMEM allocator, TMA producer (B)
 constexpr int kMaxBias = 1024;         // floats of BN shift / bias staged in shared memory
 constexpr int kStageOutBytes = 2048;   // per epilogue warp: 32 rows x 64 B output chunk for the TMA store
 constexpr int kTileM = 128;
@@ -325,7 +324,7 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map_o, uint32
 }
 
 // Epilogue of the 8 epilogue warps.  KIND selects the store path and the fused extras (EpiKind in conv_umma.cuh).
-template <int CG, int KIND>
+template <int CG, int EW, int KIND>
 __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const UmmaParams& p, SmemCtl* ctl, uint32_t tmem_base,
                                              uint32_t out_stage, int warp, int lane, uint32_t rank, int first_tile, int tile_step) {
     constexpr bool kF32 = KIND == EPI_F32;
@@ -334,13 +333,14 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
     constexpr bool kUp = KIND == EPI_UPSAMPLE;
     constexpr int CH = kF32 ? 16 : 32;
     const int quad = warp & 3;
-    const int hsel = (warp - 4) >> 2;
+    constexpr int kSplit = EW / 4;               // warps sharing a TMEM lane quadrant: they interleave the column chunks
+    const int hsel = (warp - kCtlWarps) >> 2;
     const Epilogue& ep = p.ep;
     const int Ho = p.gout.H, Wo = p.gout.W;
     const uint32_t out_rows = (uint32_t)p.out_rows;
     const int nchunks = p.BN / CH;
     const int nnt_shift = p.nnt_shift, BN = p.BN, ldc = ep.ldc;
-    const uint32_t stg = out_stage + (uint32_t)(warp - 4) * kStageOutBytes;
+    const uint32_t stg = out_stage + (uint32_t)(warp - kCtlWarps) * kStageOutBytes;
     const uint32_t stg_row = stg + lane * 64;
     const uint32_t swz = (uint32_t)((lane >> 1) & 3);
     const uint32_t acc_full0 = smem_u32(&ctl->acc_full[0]), acc_empty0 = smem_u32(&ctl->acc_empty[0]);
@@ -367,6 +367,12 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
                 ux = (int)rem - uy * Wo;
             }
         }
+        uint32_t up_q[4] = {0u, 0u, 0u, 0u};          // kUp: top-left destination pixel of rows (lane >> 2) + 8k, or ~0 if past the end
+        if constexpr (kUp) {
+            const uint32_t q00 = valid ? (uint32_t)((us * 2 * Ho + 2 * uy) * (2 * Wo) + 2 * ux) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) up_q[k] = __shfl_sync(0xFFFFFFFFu, q00, (lane >> 2) + 8 * k);
+        }
         const __half* res_row = nullptr;
         uint4 rnext[4] = {};
         if constexpr (kRes) {
@@ -383,7 +389,7 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
 #ifdef BYOLO_DBG_HOOKS
         if (!(p.dbg & 2))
 #endif
-        for (int ch = hsel; ch < nchunks; ch += 2) {
+        for (int ch = hsel; ch < nchunks; ch += kSplit) {
             const int c0 = ch * CH;                  // column inside the tile
             uint32_t raw[32];
             if constexpr (kF32) tmem_ld16(taddr + c0, raw); else tmem_ld32(taddr + c0, raw);
@@ -391,8 +397,8 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
             if constexpr (kRes) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-                if (valid && ch + 2 < nchunks) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res_row + (ch + 2) * CH);
+                if (valid && ch + kSplit < nchunks) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res_row + (ch + kSplit) * CH);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
                 }
@@ -413,17 +419,33 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
             }
             if constexpr (!kUp) {
                 stage_and_store(map_o, stg, stg_row, swz, lane, o4, c, m_tile * kTileM + quad * 32);
-            } else if (valid) {   // nearest-neighbour x2 -> four destination pixels
+            } else {
+                // nearest-neighbour x2: every row goes to four destination pixels.  The chunk is transposed through the
+                // staging block so that one store instruction writes 8 rows x 64 contiguous bytes (full 32 B sectors).
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t dst = stg_row + (((uint32_t)j ^ swz) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o4[j].x), "r"(o4[j].y), "r"(o4[j].z), "r"(o4[j].w) : "memory");
+                }
+                __syncwarp();
                 __half* ob = reinterpret_cast<__half*>(ep.out);
 #pragma unroll
-                for (int dy = 0; dy < 2; ++dy)
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t rr = (uint32_t)(lane >> 2) + 8u * k, jj = (uint32_t)lane & 3u;
+                    uint4 v;
+                    const uint32_t src = stg + rr * 64 + ((jj ^ ((rr >> 1) & 3u)) << 4);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
+                    if (up_q[k] != 0xFFFFFFFFu) {
 #pragma unroll
-                    for (int dx = 0; dx < 2; ++dx) {
-                        const size_t q = ((size_t)us * (2 * Ho) + (2 * uy + dy)) * (2 * Wo) + (2 * ux + dx);
-                        uint4* o = reinterpret_cast<uint4*>(ob + q * ldc + c);
+                        for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) o[j] = o4[j];
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const size_t q = (size_t)up_q[k] + (size_t)(dy * 2 * Wo + dx);
+                                *reinterpret_cast<uint4*>(ob + q * ldc + c + jj * 8) = v;
+                            }
                     }
+                }
             }
         }
         tc_fence_before();
@@ -440,8 +462,8 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
 // 128 A rows and HALF of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) for both, every CTA runs
 // the epilogue of its own 128 accumulator rows.  Per SM and MMA cycle this moves 2/3 of the bytes of CG = 1.
 // AM: how the producer addresses the A operand (AMode in conv_umma.cuh).
-template <int CG, int AM>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CG, int AM, int EW>
+__global__ void __launch_bounds__((kCtlWarps + EW) * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o, const UmmaParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -451,7 +473,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     const uint32_t stage_bytes = kb_bytes * p.kbs;                // a stage holds kbs K blocks (8 MMAs per commit when kbs = 2)
     const uint32_t out_stage = ring + p.num_stages * stage_bytes;
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (ring - smem_u32(smem_raw)) + (size_t)p.num_stages * stage_bytes +
-                                              kEpiWarps * kStageOutBytes);
+                                              EW * kStageOutBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -466,12 +488,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.num_stages; ++s) {
-            mbar_init(smem_u32(&ctl->full[s]), 1);
+            mbar_init(smem_u32(&ctl->full[s]), p.bsplit ? 2 : 1);       // split: the A and the B producer warp each post their byte count
             mbar_init(smem_u32(&ctl->empty[s]), 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&ctl->acc_full[s]), 1);
-            mbar_init(smem_u32(&ctl->acc_empty[s]), kEpiWarps * CG);      // CG = 2: both CTAs' epilogues release the leader
+            mbar_init(smem_u32(&ctl->acc_empty[s]), EW * CG);      // CG = 2: both CTAs' epilogues release the leader
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -488,7 +510,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         }
     }
-    for (int i = threadIdx.x; i < (p.BN << p.nnt_shift); i += kThreads) ctl->bias[i] = __ldg(p.ep.bias + i);
+    for (int i = threadIdx.x; i < (p.BN << p.nnt_shift); i += (kCtlWarps + EW) * 32) ctl->bias[i] = __ldg(p.ep.bias + i);
     tc_fence_before();
     __syncthreads();
     if constexpr (CG == 2) cluster_sync_all();           // the peer's barriers exist before anyone signals them
@@ -514,14 +536,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
 
     if (warp == 0) {
-        // ================================ TMA producer (whole warp converged, one elected lane issues) ================
-        const int BK = p.BK, BN = p.BN, kbt = p.kb1 + p.kb2, kb1 = p.kb1, cstride = p.stride;
-        const int n_rank = (int)rank * p.b_rows * (CG - 1);                  // CG = 2: my half of B
+        // ================================ TMA producer, A operand (whole warp converged, one elected lane issues) =====
+        const int BK = p.BK, kbt = p.kb1 + p.kb2, kb1 = p.kb1, cstride = p.stride;
         const uint32_t a_bytes = p.a_bytes;
+        const bool bsplit = p.bsplit != 0;
         uint32_t stage = 0, phase = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             const int m_tile = (tile >> nnt_shift) * CG + (int)rank;
-            const int n0 = (tile & ((1 << nnt_shift) - 1)) * BN + n_rank;
             const int m0 = m_tile * kTileM;
             int cw = 0, chh = 0, cn = 0, ct = 0;          // first output pixel of the tile as tensor-map coordinates
             if constexpr (AM != A_TILED) {
@@ -541,6 +562,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             }
             int cb = 0, r = 0, s = 0;                     // channel block, filter tap (r, s)
             int b_k = 0;
+            const int n0b = (tile & ((1 << nnt_shift) - 1)) * p.BN + (int)rank * p.b_rows * (CG - 1);
             for (int kb = 0; kb < num_kb; kb += kbs) {
                 const int nkb = min(kbs, num_kb - kb);
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -555,7 +577,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                     continue;
                 }
 #endif
-                if (leader_lane && rank == 0) mbar_expect_tx(full, kb_bytes * nkb * CG);   // bytes of both CTAs land on the leader's barrier
+                if (leader_lane && rank == 0) mbar_expect_tx(full, (bsplit ? a_bytes : kb_bytes) * nkb * CG);    // bytes of both CTAs land on the leader's barrier
                 for (int j = 0; j < nkb; ++j) {
                     if (leader_lane) {
                         if constexpr (AM == A_IM2COL) {
@@ -569,7 +591,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                             if (cb < kb1) tma_a2d<CG>(sa, &map_a1, full, cb * BK, m0);
                             else tma_a2d<CG>(sa, &map_a2, full, (cb - kb1) * BK, m0);
                         }
-                        tma_a2d<CG>(sa + a_bytes, &map_b, full, b_k, n0);
+                        if (!bsplit) tma_a2d<CG>(sa + a_bytes, &map_b, full, b_k, n0b);
                     }
                     sa += kb_bytes;
                     b_k += BK;
@@ -634,7 +656,40 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                 __syncwarp();
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp == 3 && p.bsplit) {
+        // ================================ TMA producer, B operand (weights): same ring, same barriers =================
+        const int BK = p.BK, BN = p.BN;
+        const int n_rank = (int)rank * p.b_rows * (CG - 1);                  // CG = 2: my half of B
+        const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes;
+        uint32_t stage = 0, phase = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            const int n0 = (tile & ((1 << nnt_shift) - 1)) * BN + n_rank;
+            int b_k = 0;
+            for (int kb = 0; kb < num_kb; kb += kbs) {
+                const int nkb = min(kbs, num_kb - kb);
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t full = full0 + 8 * stage;
+                const bool leader_lane = elect_one();
+                uint32_t sb = ring + stage * stage_bytes + a_bytes;
+#ifdef BYOLO_DBG_HOOKS
+                if (p.dbg & 1) {
+                    if (leader_lane && rank == 0) mbar_arrive(full);
+                    __syncwarp();
+                    if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
+                    continue;
+                }
+#endif
+                if (leader_lane && rank == 0) mbar_expect_tx(full, b_bytes * nkb * CG);
+                for (int j = 0; j < nkb; ++j) {
+                    if (leader_lane) tma_a2d<CG>(sb, &map_b, full, b_k, n0);
+                    sb += kb_bytes;
+                    b_k += BK;
+                }
+                __syncwarp();
+                if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= kCtlWarps) {
         // ================================ epilogue ================================
         // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), the two warps of a quadrant interleave the column
         // chunks.  A chunk is 64 bytes of output per row (32 fp16 or 16 fp32 columns): TMEM -> registers,
@@ -644,13 +699,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         // The residual of the next chunk is requested before the current one is processed (the first one before the
         // accumulator barrier), so its latency overlaps TMEM traffic and math.
         switch (p.epi_kind) {
-            case EPI_F16: run_epilogue<CG, EPI_F16>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
-            case EPI_F16_RES: run_epilogue<CG, EPI_F16_RES>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
-            case EPI_F16_DROP: run_epilogue<CG, EPI_F16_DROP>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+            case EPI_F16: run_epilogue<CG, EW, EPI_F16>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+            case EPI_F16_RES: run_epilogue<CG, EW, EPI_F16_RES>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+            case EPI_F16_DROP: run_epilogue<CG, EW, EPI_F16_DROP>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
             default:
                 if constexpr (CG == 1 && AM == A_TILED) {
-                    if (p.epi_kind == EPI_F32) run_epilogue<CG, EPI_F32>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
-                    else run_epilogue<CG, EPI_UPSAMPLE>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
+                    if (p.epi_kind == EPI_F32) run_epilogue<CG, EW, EPI_F32>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
+                    else run_epilogue<CG, EW, EPI_UPSAMPLE>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
                 }
                 break;
         }
@@ -816,13 +871,25 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.b_bytes = p.b_rows * swz;
     // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for a CTA pair)
     p.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((kTileM * p.cg) >> 4) << 24);
-    const int budget = 227 * 1024 - 1024 - (int)sizeof(SmemCtl) - kEpiWarps * kStageOutBytes - 64;
+    static const int ew_env = getenv("BYOLO_EW") ? atoi(getenv("BYOLO_EW")) : 0;
+    static const int bsplit_env = getenv("BYOLO_BSPLIT") ? atoi(getenv("BYOLO_BSPLIT")) : 1;
+    // 8 epilogue warps.  16 (BYOLO_EW=16, CG = 1 only) were measured SLOWER: the block then has to fit 96 registers per
+    // thread and the staging blocks cost a pipeline stage (profiles/r01/exp_v8_switches.txt).
+    p.epi_warps = (p.cg == 1 && ew_env == 16) ? 16 : 8;
+    p.bsplit = bsplit_env;
+    const int budget = 227 * 1024 - 1024 - (int)sizeof(SmemCtl) - p.epi_warps * kStageOutBytes - 64;
     static const int kbs_env = getenv("BYOLO_KBS") ? atoi(getenv("BYOLO_KBS")) : 0;
     const int num_kb = p.taps * (p.kb1 + p.kb2);
-    p.kbs = (kbs_env == 1 || num_kb < 2 || budget / (2 * (p.a_bytes + p.b_bytes)) < 3) ? 1 : 2;   // >= 3 stages of 2 K blocks
+    // K blocks per stage: every stage costs one barrier round trip and one tcgen05.commit (~400 cycles of issue
+    // overhead measured on the short layers), so a stage should carry >= 8 MMAs: 2 blocks of 64 channels or 4 of 32 -
+    // as long as >= 3 stages still fit.
+    p.kbs = 1;
+    if (kbs_env != 1)
+        for (int cand = (p.BK == 64 ? 2 : 4); cand >= 2; cand /= 2)
+            if (num_kb >= cand && budget / (cand * (p.a_bytes + p.b_bytes)) >= 3) { p.kbs = cand; break; }
     const int stage_bytes = p.kbs * (p.a_bytes + p.b_bytes);
     p.num_stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
-    L->smem_bytes = p.num_stages * stage_bytes + 1024 + sizeof(SmemCtl) + kEpiWarps * kStageOutBytes + 64;
+    L->smem_bytes = p.num_stages * stage_bytes + 1024 + sizeof(SmemCtl) + p.epi_warps * kStageOutBytes + 64;
 
     const uint32_t one[5] = {1, 1, 1, 1, 1};
     p.num_m_tiles = (int)((p.out_rows + kTileM - 1) / kTileM);
@@ -873,11 +940,15 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
         auto set = [](const void* f) {
             if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         };
-        set((const void*)conv_umma_kernel<1, A_TILED>);
-        set((const void*)conv_umma_kernel<1, A_IM2COL>);
-        set((const void*)conv_umma_kernel<1, A_STACK1>);
-        set((const void*)conv_umma_kernel<1, A_STACK2>);
-        set((const void*)conv_umma_kernel<2, A_IM2COL>);
+        set((const void*)conv_umma_kernel<1, A_TILED, 16>);
+        set((const void*)conv_umma_kernel<1, A_IM2COL, 16>);
+        set((const void*)conv_umma_kernel<1, A_STACK1, 16>);
+        set((const void*)conv_umma_kernel<1, A_STACK2, 16>);
+        set((const void*)conv_umma_kernel<2, A_IM2COL, 8>);
+        set((const void*)conv_umma_kernel<1, A_TILED, 8>);
+        set((const void*)conv_umma_kernel<1, A_IM2COL, 8>);
+        set((const void*)conv_umma_kernel<1, A_STACK1, 8>);
+        set((const void*)conv_umma_kernel<1, A_STACK2, 8>);
     });
     BY_CUDA(attr_err);
     return 0;
@@ -886,7 +957,7 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
 int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(L.grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3((kCtlWarps + L.p.epi_warps) * 32);
     cfg.dynamicSmemBytes = L.smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -901,15 +972,19 @@ int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
         attr[1].val.clusterDim.z = 1;
         cfg.numAttrs = 2;
         BY_REQUIRE(L.p.amode == A_IM2COL, "CTA pairs are only used for 3x3 convs");
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_IM2COL>, L.a1, L.a2, L.b, L.o, L.p));
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_IM2COL, 8>, L.a1, L.a2, L.b, L.o, L.p));
     } else if (L.p.amode == A_IM2COL) {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL>, L.a1, L.a2, L.b, L.o, L.p));
+        if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL, 16>, L.a1, L.a2, L.b, L.o, L.p));
     } else if (L.p.amode == A_STACK1) {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1>, L.a1, L.a2, L.b, L.o, L.p));
+        if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1, 16>, L.a1, L.a2, L.b, L.o, L.p));
     } else if (L.p.amode == A_STACK2) {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2>, L.a1, L.a2, L.b, L.o, L.p));
+        if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2, 16>, L.a1, L.a2, L.b, L.o, L.p));
     } else {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED>, L.a1, L.a2, L.b, L.o, L.p));
+        if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED, 16>, L.a1, L.a2, L.b, L.o, L.p));
     }
     return 0;
 }

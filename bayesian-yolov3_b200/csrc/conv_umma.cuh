@@ -31,6 +31,8 @@ struct UmmaParams {
     int BN, BK, num_stages;
     int kbs;                       // K blocks per pipeline stage (1 or 2): one barrier round trip / tcgen05.commit per stage
     int cg;                        // CTAs per tile: 1, or 2 (cta_group::2 pair, M = 256)
+    int epi_warps;                 // 8 | 16 epilogue warps (block = 4 control warps + these)
+    int bsplit;                    // 1: warp 3 issues the B (weight) loads, warp 0 only A; 0: warp 0 issues both
     int b_rows;                    // rows of B each CTA stages (BN / cg)
     int a_bytes, b_bytes;          // bytes of one A / B stage tile
     int taps;                      // 1 | 9

@@ -884,9 +884,13 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     // overhead measured on the short layers), so a stage should carry >= 8 MMAs: 2 blocks of 64 channels or 4 of 32 -
     // as long as >= 3 stages still fit.
     p.kbs = 1;
-    if (kbs_env != 1)
+    if (kbs_env >= 2) {                                   // experiment: force it wherever two stages still fit
+        if (num_kb >= kbs_env && budget / (kbs_env * (p.a_bytes + p.b_bytes)) >= 2) p.kbs = kbs_env;
+        else if (num_kb >= 2 && budget / (2 * (p.a_bytes + p.b_bytes)) >= 3) p.kbs = 2;
+    } else if (kbs_env != 1) {
         for (int cand = (p.BK == 64 ? 2 : 4); cand >= 2; cand /= 2)
             if (num_kb >= cand && budget / (cand * (p.a_bytes + p.b_bytes)) >= 3) { p.kbs = cand; break; }
+    }
     const int stage_bytes = p.kbs * (p.a_bytes + p.b_bytes);
     p.num_stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
     L->smem_bytes = p.num_stages * stage_bytes + 1024 + sizeof(SmemCtl) + p.epi_warps * kStageOutBytes + 64;

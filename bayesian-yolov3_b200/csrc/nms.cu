@@ -17,9 +17,19 @@
 //          3. gather the kept rows, zero-fill the tail, write indices and count.
 // Because "any earlier kept box overlaps" is order independent, the parallel evaluation selects exactly the boxes
 // the sequential algorithm selects.
+//
+// A batch of B images would occupy only B of the 148 SMs, so an image is handled by a thread-block CLUSTER of CS CTAs
+// (CS = 1, 2, 4 or 8): every CTA keeps the full state (sorted keys, kept list) and runs the cheap phases redundantly,
+// while the pair tests - phase (A) over the kept list and the rows of the bit matrix in (B), >half of the time at CS = 1 -
+// are split across the cluster and exchanged through distributed shared memory (two cluster barriers per batch).
 #include <algorithm>
+#include <cstdlib>
+
+#include <cooperative_groups.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace byolo {
 
@@ -38,7 +48,7 @@ __device__ __forceinline__ uint32_t ordered_key(float f) {
 // (it returns 0 before looking at the other box); it is stored as (+inf, +inf, -inf, -inf) so that the first
 // interval test of iou_gt rejects it without a separate area check.
 struct __align__(16) Box4 { float ymin, xmin, ymax, xmax; };
-constexpr size_t kAuxBytes = (sizeof(Box4) + 4) * (kBatch + kMaxOut) + 4u * (kBatch * kWords + 8 * kWords) + 4u * kMaxOut;
+constexpr size_t kAuxBytes = (sizeof(Box4) + 4) * (kBatch + kMaxOut) + 4u * (kBatch * kWords + 9 * kWords) + 4u * kMaxOut;
 
 __device__ __forceinline__ void load_box(const float* r, Box4* b, float* area) {
     Box4 t;
@@ -92,12 +102,16 @@ __device__ void bitonic_sort(uint32_t* key_hi, uint16_t* key_lo, int NP) {
     }
 }
 
+template <int CS>
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float thr, int max_out, int NP,
            size_t region0, float* __restrict__ out_rows, int* __restrict__ out_idx, int* __restrict__ out_count) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* rows = rows_all + (size_t)blockIdx.x * N * D;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = CS > 1 ? (int)cluster.block_rank() : 0;      // my share of the pair tests
+    const int img = blockIdx.x / CS;
+    const float* rows = rows_all + (size_t)img * N * D;
     // region 0: score histogram (top-K selection), then score keys during the sort, then the scan-phase scratch;
     // region 1: the candidate indices, which the sort leaves in selection-priority order.
     uint32_t* key_hi = reinterpret_cast<uint32_t*>(sm);                 // [NP]
@@ -112,8 +126,9 @@ nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float 
     uint32_t* dead = mask + kBatch * kWords;                            // [kWords] suppressed by earlier batches / padding
     uint32_t* contested = dead + kWords;                                // [kWords] has a potential suppressor inside the batch
     uint32_t* has_row = contested + kWords;                             // [kWords] suppresses somebody inside the batch
-    uint32_t* selw = has_row + kWords;                                  // [kWords] final selection of the batch
-    int* kept_idx = reinterpret_cast<int*>(selw + 5 * kWords);          // [max_out]
+    uint32_t* selw = has_row + kWords;                                  // [2 * kWords] final selection of the batch + rank offsets
+    uint32_t* dpart = selw + 2 * kWords;                                // [kWords] phase (A) hits found by THIS CTA
+    int* kept_idx = reinterpret_cast<int*>(selw + 6 * kWords);          // [max_out]
     __shared__ int s_kept, s_cut_bin, s_ncand, s_fill;
     __shared__ int s_warp_sum[32];
 
@@ -198,41 +213,63 @@ nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float 
                 cand[tid] = b;
                 cand_area[tid] = a;
             }
-            if (tid < kWords) { dead[tid] = 0u; contested[tid] = 0u; has_row[tid] = 0u; }
+            if (tid < kWords) { dead[tid] = 0u; contested[tid] = 0u; has_row[tid] = 0u; dpart[tid] = 0u; }
+            if (CS > 1)                                    // peers only deliver the non-zero words of the bit matrix
+                for (int i = tid; i < kBatch * kWords; i += kNmsThreads) mask[i] = 0u;
             __syncthreads();
-            {   // (A) two threads per candidate, each scanning half of the kept list
-                const int c = tid & (kBatch - 1), part = tid >> 9;
-                const int half = (kept_before + 1) >> 1;
-                const int j0 = part * half, j1 = min(kept_before, j0 + half);
+            {   // (A) two threads per candidate and CTA, each scanning one of the 2*CS parts of the kept list
+                const int c = tid & (kBatch - 1), part = crank * 2 + (tid >> 9);
+                const int chunk = (kept_before + 2 * CS - 1) / (2 * CS);
+                const int j0 = part * chunk, j1 = min(kept_before, j0 + chunk);
                 const Box4 me = cand[c];
                 const float my_area = cand_area[c];
                 bool hit = false;
                 if (c < nb)
                     for (int j = j0; j < j1; ++j)
                         if (iou_gt(me, my_area, kept[j], kept_area[j], thr)) { hit = true; break; }
-                if (hit || c >= nb) atomicOr(&dead[c >> 5], 1u << (c & 31));
+                if (hit || c >= nb) atomicOr(&dpart[c >> 5], 1u << (c & 31));
             }
             __syncthreads();
-            // (B) suppression matrix, one ballot per 32 pairs: row k, word w, lane l <-> candidate c = 32w + l
-            for (int k = warp; k < kBatch; k += kNmsThreads / 32) {
-                const bool k_alive = !((dead[k >> 5] >> (k & 31)) & 1u);
-                const int w0 = k >> 5;
-                if (lane < w0 || !k_alive) mask[k * kWords + (lane & (kWords - 1))] = 0u;
-                if (!k_alive) continue;                                  // warp-uniform
-                const Box4 bk = cand[k];
-                const float ak = cand_area[k];
-                uint32_t any = 0u;
-                for (int w = w0; w < kWords; ++w) {
-                    const int c = w * 32 + lane;
-                    const bool bit = (c > k) && !((dead[w] >> lane) & 1u) && iou_gt(cand[c], cand_area[c], bk, ak, thr);
-                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
-                    if (lane == 0) mask[k * kWords + w] = word;
-                    any |= word;
-                    if (word && lane == 0) atomicOr(&contested[w], word);
+            if (CS > 1) {
+                cluster.sync();                            // every CTA's hits are in its dpart[]; all masks are zeroed
+                if (tid < kWords * CS) atomicOr(&dead[tid & (kWords - 1)], cluster.map_shared_rank(dpart, tid / kWords)[tid & (kWords - 1)]);
+            } else if (tid < kWords) {
+                dead[tid] = dpart[tid];
+            }
+            __syncthreads();
+            // (B) suppression matrix, one ballot per 32 pairs: row k, word w, lane l <-> candidate c = 32w + l.  The rows
+            // are dealt round-robin to the CTAs of the cluster; a CTA delivers its non-zero words to every CTA.
+            {
+                uint32_t* mask_to = mask;
+                uint32_t* contested_to = contested;
+                uint32_t* has_row_to = has_row;
+                if (CS > 1 && lane < CS) {                 // lane l of every warp writes to CTA l
+                    mask_to = cluster.map_shared_rank(mask, lane);
+                    contested_to = cluster.map_shared_rank(contested, lane);
+                    has_row_to = cluster.map_shared_rank(has_row, lane);
                 }
-                if (any && lane == 0) atomicOr(&has_row[k >> 5], 1u << (k & 31));
+                const bool writer = CS > 1 ? (lane < CS) : (lane == 0);
+                for (int it = 0, k = warp; k < kBatch; k += kNmsThreads / 32, ++it) {
+                    if (CS > 1 && (it % CS) != crank) continue;              // warp-uniform
+                    const bool k_alive = !((dead[k >> 5] >> (k & 31)) & 1u);
+                    const int w0 = k >> 5;
+                    if (CS == 1 && (lane < w0 || !k_alive)) mask[k * kWords + (lane & (kWords - 1))] = 0u;
+                    if (!k_alive) continue;                                  // warp-uniform
+                    const Box4 bk = cand[k];
+                    const float ak = cand_area[k];
+                    uint32_t any = 0u;
+                    for (int w = w0; w < kWords; ++w) {
+                        const int c = w * 32 + lane;
+                        const bool bit = (c > k) && !((dead[w] >> lane) & 1u) && iou_gt(cand[c], cand_area[c], bk, ak, thr);
+                        const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
+                        if (writer && (CS == 1 || word)) mask_to[k * kWords + w] = word;
+                        any |= word;
+                        if (word && writer) atomicOr(&contested_to[w], word);
+                    }
+                    if (any && writer) atomicOr(&has_row_to[k >> 5], 1u << (k & 31));
+                }
             }
-            __syncthreads();
+            if (CS > 1) cluster.sync(); else __syncthreads();
             // (C) resolve.  A candidate that nobody in the batch can suppress and that suppresses nobody is kept without
             // looking at the order; only the others (bit in `contested` or `has_row`) go through the sequential walk.
             if (warp == 0) {
@@ -294,14 +331,15 @@ nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float 
 
     // ---- 3. gather ----
     const int n_kept = s_kept;
-    float* orow = out_rows + (size_t)blockIdx.x * max_out * D;
-    for (int e = tid; e < max_out * D; e += kNmsThreads) {
+    float* orow = out_rows + (size_t)img * max_out * D;
+    for (int e = crank * kNmsThreads + tid; e < max_out * D; e += kNmsThreads * CS) {      // every CTA holds the full result
         const int k = e / D, c = e - k * D;
         orow[e] = (k < n_kept) ? rows[(size_t)kept_idx[k] * D + c] : 0.f;
     }
-    if (out_idx)
-        for (int k = tid; k < max_out; k += kNmsThreads) out_idx[(size_t)blockIdx.x * max_out + k] = (k < n_kept) ? kept_idx[k] : -1;
-    if (tid == 0 && out_count) out_count[blockIdx.x] = n_kept;
+    if (out_idx && crank == 0)
+        for (int k = tid; k < max_out; k += kNmsThreads) out_idx[(size_t)img * max_out + k] = (k < n_kept) ? kept_idx[k] : -1;
+    if (tid == 0 && crank == 0 && out_count) out_count[img] = n_kept;
+    if (CS > 1) cluster.sync();                            // nobody leaves while a peer may still touch its shared memory
 }
 
 size_t nms_workspace_bytes(int, int) { return 0; }
@@ -317,13 +355,60 @@ int launch_nms(const float* rows, int B, int N, int D, int obj_idx, float iou_th
     while (NP < N) NP <<= 1;
     const size_t region0 = std::max({(size_t)NP * 4, kAuxBytes, N > 4096 ? (size_t)65536 * 2 : (size_t)0});
     const size_t smem = region0 + (size_t)NP * 2;
-    static bool attr_done = false;
-    if (!attr_done) {
-        BY_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        attr_done = true;
-    }
     BY_REQUIRE(smem <= 227 * 1024 - 1024, "NMS shared memory budget exceeded");
-    nms_kernel<<<B, kNmsThreads, smem, st>>>(rows, N, D, obj_idx, iou_thr, max_out, NP, region0, out_rows, out_idx, out_count);
+    // cluster size: as many CTAs per image as keep all images resident at once (148 SMs, one CTA per SM)
+    const int cs_env = getenv("BYOLO_NMS_CS") ? atoi(getenv("BYOLO_NMS_CS")) : 0;      // tests force every cluster size
+    static int max_clusters[4] = {-1, -1, -1, -1};          // co-resident clusters of size 1 << i at this smem size (queried once)
+    static size_t queried_smem = 0;
+    auto launch = [&](auto kernel, int cs) -> cudaError_t {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(B * cs);
+        cfg.blockDim = dim3(kNmsThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, rows, N, D, obj_idx, iou_thr, max_out, NP, region0, out_rows, out_idx, out_count);
+    };
+    auto occupancy = [&](auto kernel, int cs) -> int {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess) return 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(cs * 64);
+        cfg.blockDim = dim3(kNmsThreads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return n;
+    };
+    if (queried_smem != smem) {
+        max_clusters[0] = occupancy(nms_kernel<1>, 1);
+        max_clusters[1] = occupancy(nms_kernel<2>, 2);
+        max_clusters[2] = occupancy(nms_kernel<4>, 4);
+        max_clusters[3] = occupancy(nms_kernel<8>, 8);
+        queried_smem = smem;
+    }
+    int cs = 1;
+    for (int i = 3; i >= 1; --i)
+        if (max_clusters[i] >= B) { cs = 1 << i; break; }
+    if (cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8) cs = cs_env;
+    cudaError_t err;
+    if (cs == 8) err = launch(nms_kernel<8>, 8);
+    else if (cs == 4) err = launch(nms_kernel<4>, 4);
+    else if (cs == 2) err = launch(nms_kernel<2>, 2);
+    else err = launch(nms_kernel<1>, 1);
+    BY_CUDA(err);
     BY_CUDA(cudaGetLastError());
     return 0;
 }

@@ -86,7 +86,13 @@ def stress_rows(B, seed, N=22743, D=23, obj_idx=14, img=608):
     return rows
 
 
-def test_nms_stress_full_size_bit_exact():
+@pytest.mark.parametrize('cluster', [0, 1, 2, 4, 8])
+def test_nms_stress_full_size_bit_exact(cluster, monkeypatch):
+    """cluster = CTAs per image (0: the library's own choice); every split of the pair tests must select the same boxes."""
+    if cluster:
+        monkeypatch.setenv('BYOLO_NMS_CS', str(cluster))
+    else:
+        monkeypatch.delenv('BYOLO_NMS_CS', raising=False)
     rows = stress_rows(4, 105)
     boxes, cnt, idx = _nms_gpu(rows, 14)
     for b in range(rows.shape[0]):
@@ -98,7 +104,9 @@ def test_nms_stress_full_size_bit_exact():
     assert cnt.min() == 1000                                    # generator guarantees >= 1000 survivors
 
 
-def test_nms_edge_cases():
+@pytest.mark.parametrize('cluster', [1, 8])
+def test_nms_edge_cases(cluster, monkeypatch):
+    monkeypatch.setenv('BYOLO_NMS_CS', str(cluster))
     rng = np.random.default_rng(5)
     # all boxes identical -> 1 survivor; zero-area boxes never suppress; tiny N; max_out smaller than survivors
     rows = np.zeros((3, 70, 7), np.float32)

@@ -1,12 +1,12 @@
 #!/bin/bash
-# Per-layer times under experiment switches (library built with -DBYOLO_DBG_HOOKS).
+# Per-layer times under experiment switches.
 mkdir -p gpurun_out
 run() { # tag, env...
   local tag=$1; shift
-  env "$@" timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --layers > gpurun_out/exp_$tag.json 2> gpurun_out/exp_$tag.txt
-  echo "$tag exit $? $(python -c "import json;print(json.load(open('gpurun_out/exp_$tag.json'))['value'])" 2>/dev/null)"
+  env "$@" timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --layers > gpurun_out/exp_$tag.json 2> gpurun_out/exp_$tag.txt
+  echo "$tag exit $? $(python -c "import json;d=json.load(open('gpurun_out/exp_$tag.json'));print(d['value'], d['breakdown_ms'])" 2>/dev/null)"
 }
 run base A=1
-run ew16 BYOLO_EW=16
-run nosplit BYOLO_BSPLIT=0
-run kbs1 BYOLO_KBS=1
+run kbs3 BYOLO_KBS=3
+run nms1 BYOLO_NMS_CS=1
+run nms4 BYOLO_NMS_CS=4

@@ -1,5 +1,5 @@
 // K2: head-output split + per-sample transforms + reduction over the T Monte-Carlo samples + anchor decode, writing
-// each row directly at its final concat_bbox position.  One thread per (image, anchor).
+// each row at its final concat_bbox position (staged in shared memory, stored coalesced).  One thread per (image, anchor).
 //   split              /root/reference/lib_yolo/layers.py:11-84
 //   standard decode    layers.py:191-258      row = [y0,x0,y1,x1, obj, cls..]
 //   aleatoric decode   layers.py:261-346      row = [y0,x0,y1,x1, var*4, prod var, obj, H(obj), cls.., H(cls), layer, prior]
@@ -53,9 +53,40 @@ __device__ float det4(float a[4][4]) {
     return det;
 }
 
-__global__ void __launch_bounds__(128) decode_kernel(const DecodeProblem p) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)p.B * p.N) return;
+constexpr int kDecThreads = 128;
+constexpr int kMaxD = 21 + kMaxCls;          // widest row (epistemic)
+
+// Loads the 2*(5+C) (or 5+C) raw values of one anchor of one sample.  The block is 8-byte aligned for the aleatoric /
+// epistemic layouts (an even number of floats per prior, maps 16 floats wide), so it is read as float2.
+template <int NMAX>
+__device__ __forceinline__ void load_block(const float* __restrict__ v, int n, bool vec2, float* dst) {
+    if (vec2) {
+#pragma unroll
+        for (int i = 0; i < NMAX; i += 2)
+            if (i < n) {
+                const float2 f = __ldg(reinterpret_cast<const float2*>(v + i));
+                dst[i] = f.x;
+                dst[i + 1] = f.y;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i)
+            if (i < n) dst[i] = __ldg(v + i);
+    }
+}
+
+// CC = compile-time class count (2: the reference default, everything stays in registers) or 0 = run-time p.cls_cnt.
+template <int CC>
+__global__ void __launch_bounds__(kDecThreads) decode_kernel(const DecodeProblem p) {
+    // rows of the block's 128 consecutive anchors are contiguous in the output: they are staged in shared memory
+    // (row pitch D is odd for every variant at cls_cnt 2 -> conflict-free) and leave as coalesced stores
+    extern __shared__ float srows[];
+    const long long gid0 = (long long)blockIdx.x * kDecThreads;
+    const long long gid = gid0 + threadIdx.x;
+    const long long total = (long long)p.B * p.N;
+    const bool active = gid < total;
+    float* out = srows + threadIdx.x * p.D;
+    if (active) {
     const int b = (int)(gid / p.N);
     int a = (int)(gid % p.N);
     int j = 0;
@@ -68,16 +99,20 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeProblem p) {
     const int prior = a / (lh * lw);
     const int cell = a - prior * lh * lw;
     const int row = cell / lw, col = cell - row * lw;
-    const int C = p.cls_cnt;
+    const int C = CC ? CC : p.cls_cnt;
+    constexpr int kC = CC ? CC : kMaxCls;      // array extents
     const int block = p.variant == 0 ? 5 + C : 2 * (5 + C);
+    const bool vec2 = (block % 2 == 0) && (p.ld[j] % 2 == 0);
     const float pw = p.prior_w[j * 3 + prior], ph = p.prior_h[j * 3 + prior];
-    float* out = p.rows + gid * p.D;
     float tx, ty, tw, th;      // (mean) t-space location
+    const long long plane = (long long)(lh + 2 * pad) * (lw + 2 * pad);
+    const float* v0 = p.raw[j] + ((long long)(row + pad) * (lw + 2 * pad) + col + pad) * p.ld[j] + prior * block;
 
     if (p.variant != 2) {
-        const float* v = p.raw[j] + ((long long)(b * (lh + 2 * pad) + row + pad) * (lw + 2 * pad) + col + pad) * p.ld[j] + prior * block;
+        float v[2 * (5 + kC)];
+        load_block<2 * (5 + kC)>(v0 + (long long)b * plane * p.ld[j], block, vec2, v);
         tx = v[0]; ty = v[1]; tw = v[2]; th = v[3];
-        float cls[kMaxCls];
+        float cls[kC];
         if (p.variant == 0) {
             out[4] = sigmoidf_(v[4]);
             softmax_(v + 5, C, cls);
@@ -102,12 +137,18 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeProblem p) {
     } else {
         const int T = p.T;
         float s_loc[4] = {0, 0, 0, 0}, s_var[4] = {0, 0, 0, 0}, s_out[4][4];
-        float s_obj = 0.f, s_obj_h = 0.f, s_cls[kMaxCls], s_cls_h = 0.f;
+        float s_obj = 0.f, s_obj_h = 0.f, s_cls[kC], s_cls_h = 0.f;
         for (int i = 0; i < 4; ++i)
             for (int k = 0; k < 4; ++k) s_out[i][k] = 0.f;
         for (int i = 0; i < C; ++i) s_cls[i] = 0.f;
+        // the next sample's values are requested before the current one is processed (the loop is latency bound)
+        float v[2 * (5 + kC)], vn[2 * (5 + kC)];
+        const float* vt = v0 + (long long)b * T * plane * p.ld[j];
+        load_block<2 * (5 + kC)>(vt, block, vec2, vn);
         for (int t = 0; t < T; ++t) {
-            const float* v = p.raw[j] + ((long long)((b * T + t) * (lh + 2 * pad) + row + pad) * (lw + 2 * pad) + col + pad) * p.ld[j] + prior * block;
+#pragma unroll
+            for (int i = 0; i < 2 * (5 + kC); ++i) v[i] = vn[i];
+            if (t + 1 < T) load_block<2 * (5 + kC)>(vt + (long long)(t + 1) * plane * p.ld[j], block, vec2, vn);
             float loc[4];
             for (int i = 0; i < 4; ++i) { loc[i] = v[i]; s_loc[i] += loc[i]; s_var[i] += expf(v[4 + i]); }
             for (int i = 0; i < 4; ++i)
@@ -115,7 +156,7 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeProblem p) {
             const float obj = sigmoidf_(v[8]);
             s_obj += obj;
             s_obj_h += logistic_entropy(obj);
-            float cls[kMaxCls];
+            float cls[kC];
             softmax_(v + 10, C, cls);
             for (int i = 0; i < C; ++i) s_cls[i] += cls[i];
             s_cls_h += softmax_entropy(cls, C);
@@ -144,7 +185,7 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeProblem p) {
         out[14] = obj_mean;
         out[15] = obj_h - s_obj_h / fT;
         out[16] = obj_h;
-        float cm[kMaxCls];
+        float cm[kC];
         for (int i = 0; i < C; ++i) { cm[i] = s_cls[i] / fT; out[17 + i] = cm[i]; }
         const float cls_h = softmax_entropy(cm, C);
         out[17 + C] = cls_h - s_cls_h / fT;
@@ -160,12 +201,21 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeProblem p) {
     out[1] = x - w2;
     out[2] = y + h2;
     out[3] = x + w2;
+    }
+    __syncthreads();
+    const long long nvals = min((long long)kDecThreads, total - gid0) * p.D;
+    float* dst = p.rows + gid0 * p.D;
+    for (int i = threadIdx.x; i < nvals; i += kDecThreads) dst[i] = srows[i];
 }
 
 int launch_decode(const DecodeProblem& p, cudaStream_t st) {
     BY_REQUIRE(p.cls_cnt >= 1 && p.cls_cnt <= kMaxCls, "cls_cnt out of range");
     const long long total = (long long)p.B * p.N;
-    decode_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(p);
+    BY_REQUIRE(p.D <= kMaxD, "row width out of range");
+    const int grid = (int)((total + kDecThreads - 1) / kDecThreads);
+    const size_t smem = sizeof(float) * kDecThreads * p.D;
+    if (p.cls_cnt == 2) decode_kernel<2><<<grid, kDecThreads, smem, st>>>(p);
+    else decode_kernel<0><<<grid, kDecThreads, smem, st>>>(p);
     BY_CUDA(cudaGetLastError());
     return 0;
 }

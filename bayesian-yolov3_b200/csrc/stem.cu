@@ -101,14 +101,15 @@ stem_mma_kernel(const float* __restrict__ img, int H, int W, int num_tiles, cons
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[nt][j] = bs[nt][j & 1];      // BN shift: the accumulator starts from it
+            for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
             mma16816(acc[nt], a[0], bf[0][nt][0], bf[0][nt][1]);
             mma16816(acc[nt], a[1], bf[1][nt][0], bf[1][nt][1]);
         }
         __syncwarp();                                    // the previous tile has left the staging block
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-            float v0 = acc[nt][0], v1 = acc[nt][1], v2 = acc[nt][2], v3 = acc[nt][3];
+            float v0 = acc[nt][0] + bs[nt][0], v1 = acc[nt][1] + bs[nt][1];
+            float v2 = acc[nt][2] + bs[nt][0], v3 = acc[nt][3] + bs[nt][1];
             v0 = fmaxf(v0, 0.1f * v0); v1 = fmaxf(v1, 0.1f * v1);
             v2 = fmaxf(v2, 0.1f * v2); v3 = fmaxf(v3, 0.1f * v3);
             *reinterpret_cast<__half2*>(so + g * kOutPitch + nt * 8 + 2 * t) = __floats2half2_rn(v0, v1);

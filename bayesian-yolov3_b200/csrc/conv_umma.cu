@@ -826,6 +826,23 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.kb1 = C1 / p.BK;
     p.kb2 = C2 / p.BK;
     p.BN = std::min(q.cout_pad, 256);
+    {
+        // Wave quantisation: a layer runs ceil(tiles / resident tiles) rounds of tiles.  Small-M layers (19x19, 38x38 maps
+        // of a 16-image batch) fill 1.24 / 2.46 rounds with 256-wide tiles; 128-wide tiles cost the same MMA rate
+        // (tools/micro/mma_rate: 4093 MAC/cycle/SM at N = 128 and 256) and waste less of the last round.
+        int dev_ = 0, sms_ = 148;
+        if (cudaGetDevice(&dev_) == cudaSuccess) cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
+        const long long m_rows = (long long)g.S * (g.H / q.stride) * (g.W / q.stride);
+        const bool pair = q.k == 3 && q.stride == 1 && C1 % 64 == 0 && C2 % 64 == 0;        // CTA pairs (decided below)
+        const long long m_units = (m_rows + (pair ? 255 : 127)) / (pair ? 256 : 128);
+        const int slots = pair ? sms_ / 2 : sms_;
+        static const int bn_env = getenv("BYOLO_BN") ? atoi(getenv("BYOLO_BN")) : 0;      // 256: never narrow the tile
+        if (q.cout_pad >= 256 && q.cout_pad % 256 == 0 && bn_env != 256) {
+            const long long r256 = (m_units * (q.cout_pad / 256) + slots - 1) / slots * 2;      // cost in 128-column units
+            const long long r128 = (m_units * (q.cout_pad / 128) + slots - 1) / slots;
+            if (r128 * 10 <= r256 * 9) p.BN = 128;       // only when a tenth of the rounds goes away (narrow tiles reload A twice as often)
+        }
+    }
     BY_REQUIRE(q.cout_pad % p.BN == 0, "cout_pad must be a multiple of the N tile");
     p.num_n_tiles = q.cout_pad / p.BN;
     BY_REQUIRE((p.num_n_tiles & (p.num_n_tiles - 1)) == 0, "the number of N tiles must be a power of two");

@@ -7,6 +7,4 @@ run() { # tag, env...
   echo "$tag exit $? $(python -c "import json;d=json.load(open('gpurun_out/exp_$tag.json'));print(d['value'], d['breakdown_ms'])" 2>/dev/null)"
 }
 run base A=1
-run kbs3 BYOLO_KBS=3
-run nms1 BYOLO_NMS_CS=1
-run nms4 BYOLO_NMS_CS=4
+run bn256 BYOLO_BN=256

@@ -852,6 +852,7 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     // CTA pairs for the feed-bound shapes: 3x3 stride-1 convs with wide N tiles
     static const int cg_env = getenv("BYOLO_CG") ? atoi(getenv("BYOLO_CG")) : 0;     // 1 = force off, 2 = default policy
     p.cg = (cg_env != 1 && q.k == 3 && q.stride == 1 && p.BN >= 128 && p.BK == 64) ? 2 : 1;
+    if (cg_env == 3 && q.k == 3 && p.BN >= 64) p.cg = 2;      // experiment: every 3x3 conv (stride 2, 32-channel layers) as CTA pairs
     p.b_rows = p.BN / p.cg;
     static const int dbg_env = getenv("BYOLO_DBG") ? atoi(getenv("BYOLO_DBG")) : 0;
     p.dbg = dbg_env;

@@ -19,6 +19,16 @@ def g(r, name, default=0.0):
         return default
 
 
+def ghz(r):
+    for nm in ('sm__cycles_elapsed.avg.per_second', 'smsp__cycles_elapsed.avg.per_second', 'gpc__cycles_elapsed.avg.per_second', 'gpc__cycles_elapsed.max.per_second'):
+        if nm in col:
+            v = g(r, nm)
+            u = units[col[nm]]
+            return v * {'Ghz': 1.0, 'GHz': 1.0, 'Mhz': 1e-3, 'MHz': 1e-3, 'hz': 1e-9, 'Hz': 1e-9, 'cycle/second': 1e-9, 'cycle/nsecond': 1.0, 'cycle/usecond': 1e-3}.get(u, 1e-9)
+    return 0.0
+
+
+units = rows[1]
 out = ['ncu --set full --clock-control none; one bench step (B=16 images, T=10, 608x608), %s' % note,
        '%-26s %-5s %8s %9s %9s %8s %6s %6s %6s %6s' % ('kernel', 'layer', 'dur[us]', 'dramR[MB]', 'dramW[MB]', 'tc_pipe%', 'dram%', 'l2%', 'sm%', 'sm_GHz')]
 conv_i, tot, conv_t, conv_b = 0, 0.0, 0.0, 0.0
@@ -47,7 +57,7 @@ for r in rows[2:]:
         name[:26], layer, dur, rd, wr, g(r, 'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active') or
         g(r, 'sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active'),
         g(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'), g(r, 'lts__throughput.avg.pct_of_peak_sustained_elapsed'),
-        g(r, 'sm__throughput.avg.pct_of_peak_sustained_elapsed'), g(r, 'smsp__cycles_elapsed.avg.per_second') / 1e9 if 'smsp__cycles_elapsed.avg.per_second' in col else 0.0))
+        g(r, 'sm__throughput.avg.pct_of_peak_sustained_elapsed'), ghz(r)))
 out.append('conv launches: %d, sum duration %.1f us (%.1f%% of the step\'s kernel time), sum DRAM traffic %.1f MB' % (
     conv_i, conv_t, 100 * conv_t / tot if tot else 0, conv_b / 1e6))
 open('profiles/r01/ncu_%s_step_summary.txt' % tag, 'w').write('\n'.join(out) + '\n')

@@ -90,7 +90,7 @@ def cpu_oracle_rate(n_images, T, img, threads=None):
     return n_images / dt, torch.get_num_threads()
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -104,12 +104,12 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = per_step * args.steps / dt
     sample = '%d image(s)/step of the same workload (608x608, T=10, decode+NMS), oracle port on %d host threads' % (per_step, cores)
-    print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus,
+    emit({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus,
                       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
                       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                       'config': WORKLOAD,
                       'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
-                      'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+                      'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
 
 
 def main():
@@ -124,8 +124,19 @@ def main():
     ap.add_argument('--no-sustained', action='store_true', help='skip the 2 s sustained-rate pass')
     ap.add_argument('--layers', action='store_true', help='print the per-launch table to stderr')
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON record): whatever libraries print (e.g. "NCCL version ...") goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(record):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(record), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == 'reference':
-        return run_reference(args)
+        return run_reference(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -290,7 +301,7 @@ def main():
             res['cpu_baseline'] = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                                    'sample': '%d images of the same workload (608x608, T=10, decode+NMS) through the oracle '
                                              'port (torch CPU fp32 + numpy decode + C NMS)' % n_cpu}
-        print(json.dumps(res))
+        emit(res)
     if world > 1:
         dist.destroy_process_group()
 

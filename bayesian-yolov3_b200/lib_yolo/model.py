@@ -87,5 +87,26 @@ class Model:
             n = dl.h * dl.w
             per = [res['rows'][:, off + p * n: off + (p + 1) * n].reshape(-1, dl.h, dl.w, res['rows'].shape[-1]) for p in range(3)]
             dl.bbox = [p[0] for p in per] if self.variant == 'epistemic' else per
+            if self.variant == 'epistemic':
+                dl.det = det_maps_from_rows(res['rows'][0, off: off + 3 * n], dl.h, dl.w, self.cls_cnt)
             off += 3 * n
         return res
+
+
+def det_maps_from_rows(rows, lh, lw, cls_cnt):
+    """The per-cell statistics dict of `decode_epistemic` (reference layers.py:397-411) that vis_uncertainty.py:80-131
+    colour-maps, rebuilt from the decoded rows of ONE detection scale ([3*lh*lw, 21+C], prior-major as concat_bbox
+    writes them).  Shapes follow the reference: [lh, lw, 3(, 4 | 4,4 | C)].  The kernel exports the diagonal of the
+    epistemic covariance only (the reference's consumers index [..., i, i]); off-diagonal entries are NaN.  `ev_loc`,
+    `obj_samples` and `cls_samples` (marked irrelevant in the reference) are not exported."""
+    C = cls_cnt
+    r = np.asarray(rows).reshape(3, lh, lw, -1).transpose(1, 2, 0, 3)          # [lh, lw, prior, D]
+    cov = np.full(r.shape[:3] + (4, 4), np.nan, r.dtype)
+    for i in range(4):
+        cov[..., i, i] = r[..., 4 + i]
+    return {
+        'epi_covar_loc': cov,
+        'ale_var_loc': r[..., 8:12],
+        'obj_mean': r[..., 14], 'obj_mutual_info': r[..., 15], 'obj_entropy': r[..., 16],
+        'cls_mean': r[..., 17:17 + C], 'cls_mutual_info': r[..., 17 + C], 'cls_entropy': r[..., 18 + C],
+    }

@@ -185,3 +185,22 @@ def test_sharded_detect_equals_single_rank_gloo(n_images):
     port = 29500 + os.getpid() % 2000 + n_images
     mp.spawn(_gloo_worker, args=(2, port, n_images, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_det_maps_from_rows_follow_the_reference_dict():
+    """vis_uncertainty.py:80-131 reads det_layers[i].det[key] (layers.py:397-411): shapes [lh, lw, 3(, ...)] and the
+    values of the row columns they came from."""
+    from lib_yolo.model import det_maps_from_rows
+    lh, lw, C = 3, 5, 2
+    rng = np.random.default_rng(3)
+    rows = rng.random((3 * lh * lw, 21 + C)).astype(np.float32)
+    det = det_maps_from_rows(rows, lh, lw, C)
+    assert det['obj_mean'].shape == (lh, lw, 3) and det['cls_mean'].shape == (lh, lw, 3, C)
+    assert det['epi_covar_loc'].shape == (lh, lw, 3, 4, 4) and det['ale_var_loc'].shape == (lh, lw, 3, 4)
+    p, y, x = 2, 1, 4
+    row = rows[p * lh * lw + y * lw + x]                       # concat_bbox order inside a scale: prior, row, col
+    assert det['obj_mean'][y, x, p] == row[14] and det['obj_mutual_info'][y, x, p] == row[15] and det['obj_entropy'][y, x, p] == row[16]
+    assert np.array_equal(det['cls_mean'][y, x, p], row[17:19]) and det['cls_mutual_info'][y, x, p] == row[19]
+    assert det['cls_entropy'][y, x, p] == row[20]
+    assert np.array_equal(np.diagonal(det['epi_covar_loc'][y, x, p]), row[4:8]) and np.array_equal(det['ale_var_loc'][y, x, p], row[8:12])
+    assert np.isnan(det['epi_covar_loc'][y, x, p][0, 1])

@@ -87,11 +87,19 @@ __device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const CUtensorMap* m
             : "memory");
     }
 }
+template <int CG>
 __device__ __forceinline__ void tma_im2col_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int d, int n) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %8, %8};" ::"r"(dst),
-        "l"((uint64_t)map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"((uint16_t)0)
-        : "memory");
+    if constexpr (CG == 2) {
+        asm volatile(
+            "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %8, %8};" ::"r"(dst),
+            "l"((uint64_t)map), "r"(bar & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"((uint16_t)0)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %8, %8};" ::"r"(dst),
+            "l"((uint64_t)map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"((uint16_t)0)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -280,10 +288,11 @@ __device__ __forceinline__ void chunk_f16(const uint32_t (&raw)[32], const float
             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float m0 = ((w[i] << 16) >= thr32) ? d.keep_scale : 0.f;
-                const float m1 = (w[i] >= thr32) ? d.keep_scale : 0.f;
-                v[2 * i] = fmaf(__uint_as_float(raw[8 * g + 2 * i]), m0, b[2 * i]);
-                v[2 * i + 1] = fmaf(__uint_as_float(raw[8 * g + 2 * i + 1]), m1, b[2 * i + 1]);
+                // dropped: the shift alone; kept: x * 1/(1-p) + shift in one FFMA (predicated on the compare)
+                v[2 * i] = b[2 * i];
+                v[2 * i + 1] = b[2 * i + 1];
+                if ((w[i] << 16) >= thr32) v[2 * i] = fmaf(__uint_as_float(raw[8 * g + 2 * i]), d.keep_scale, b[2 * i]);
+                if (w[i] >= thr32) v[2 * i + 1] = fmaf(__uint_as_float(raw[8 * g + 2 * i + 1]), d.keep_scale, b[2 * i + 1]);
             }
         } else {
 #pragma unroll
@@ -583,10 +592,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                         if constexpr (AM == A_IM2COL) {
                             tma_im2col_4d<CG>(sa, &map_a1, full, cb * BK, cw, chh, cn, s, r);
                         } else if constexpr (AM == A_STACK1) {
-                            tma_im2col_5d(sa, &map_a1, full, cb * BK, cw, chh, ct, cn);
+                            tma_im2col_5d<CG>(sa, &map_a1, full, cb * BK, cw, chh, ct, cn);
                         } else if constexpr (AM == A_STACK2) {
                             if (cb < kb1) tma_a2d<CG>(sa, &map_a1, full, cb * BK, m0);
-                            else tma_im2col_5d(sa, &map_a2, full, (cb - kb1) * BK, cw, chh, ct, cn);
+                            else tma_im2col_5d<CG>(sa, &map_a2, full, (cb - kb1) * BK, cw, chh, ct, cn);
                         } else {
                             if (cb < kb1) tma_a2d<CG>(sa, &map_a1, full, cb * BK, m0);
                             else tma_a2d<CG>(sa, &map_a2, full, (cb - kb1) * BK, m0);
@@ -854,6 +863,9 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     // (measured per layer, profiles/r01/exp_v8_switches.txt: pairs win on every 3x3 conv except the 32-channel stride-1 layer)
     p.cg = (cg_env != 1 && q.k == 3 && p.BN >= 64 && (q.stride == 2 || (p.BN >= 128 && p.BK == 64))) ? 2 : 1;
     if (cg_env == 3 && q.k == 3 && p.BN >= 64) p.cg = 2;      // experiment: every 3x3 conv as CTA pairs
+    // 1x1 convs with K >= 1024 (the 1024 -> 512 layers): pairs halve the weight traffic (+8%); at K = 512 they lose 11%
+    if (cg_env != 1 && q.k == 1 && p.BN >= 256 && p.BK == 64 && C1 + C2 >= 1024 && q.ep.out_mode == OUT_DENSE) p.cg = 2;
+    if (cg_env == 4 && q.k == 1 && p.BN >= 256 && p.BK == 64 && q.ep.out_mode == OUT_DENSE) p.cg = 2;      // experiment: all wide 1x1 convs
     p.b_rows = p.BN / p.cg;
     static const int dbg_env = getenv("BYOLO_DBG") ? atoi(getenv("BYOLO_DBG")) : 0;
     p.dbg = dbg_env;
@@ -894,7 +906,7 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     static const int bsplit_env = getenv("BYOLO_BSPLIT") ? atoi(getenv("BYOLO_BSPLIT")) : 1;
     // 8 epilogue warps.  16 (BYOLO_EW=16, CG = 1 only) were measured SLOWER: the block then has to fit 96 registers per
     // thread and the staging blocks cost a pipeline stage (profiles/r01/exp_v8_switches.txt).
-    p.epi_warps = (p.cg == 1 && ew_env == 16) ? 16 : 8;
+    p.epi_warps = (p.cg == 1 && (ew_env == 16 || ew_env == 12)) ? ew_env : 8;
     p.bsplit = bsplit_env;
     const int budget = 227 * 1024 - 1024 - (int)sizeof(SmemCtl) - p.epi_warps * kStageOutBytes - 64;
     static const int kbs_env = getenv("BYOLO_KBS") ? atoi(getenv("BYOLO_KBS")) : 0;
@@ -968,6 +980,13 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
         set((const void*)conv_umma_kernel<1, A_STACK1, 16>);
         set((const void*)conv_umma_kernel<1, A_STACK2, 16>);
         set((const void*)conv_umma_kernel<2, A_IM2COL, 8>);
+        set((const void*)conv_umma_kernel<2, A_TILED, 8>);
+        set((const void*)conv_umma_kernel<2, A_STACK1, 8>);
+        set((const void*)conv_umma_kernel<2, A_STACK2, 8>);
+        set((const void*)conv_umma_kernel<1, A_TILED, 12>);
+        set((const void*)conv_umma_kernel<1, A_IM2COL, 12>);
+        set((const void*)conv_umma_kernel<1, A_STACK1, 12>);
+        set((const void*)conv_umma_kernel<1, A_STACK2, 12>);
         set((const void*)conv_umma_kernel<1, A_TILED, 8>);
         set((const void*)conv_umma_kernel<1, A_IM2COL, 8>);
         set((const void*)conv_umma_kernel<1, A_STACK1, 8>);
@@ -994,19 +1013,25 @@ int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
         attr[1].val.clusterDim.y = 1;
         attr[1].val.clusterDim.z = 1;
         cfg.numAttrs = 2;
-        BY_REQUIRE(L.p.amode == A_IM2COL, "CTA pairs are only used for 3x3 convs");
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_IM2COL, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        if (L.p.amode == A_IM2COL) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_IM2COL, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else if (L.p.amode == A_STACK1) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_STACK1, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else if (L.p.amode == A_STACK2) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_STACK2, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_TILED, 8>, L.a1, L.a2, L.b, L.o, L.p));
     } else if (L.p.amode == A_IM2COL) {
         if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else if (L.p.epi_warps == 12) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL, 12>, L.a1, L.a2, L.b, L.o, L.p));
         else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL, 16>, L.a1, L.a2, L.b, L.o, L.p));
     } else if (L.p.amode == A_STACK1) {
         if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else if (L.p.epi_warps == 12) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1, 12>, L.a1, L.a2, L.b, L.o, L.p));
         else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1, 16>, L.a1, L.a2, L.b, L.o, L.p));
     } else if (L.p.amode == A_STACK2) {
         if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else if (L.p.epi_warps == 12) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2, 12>, L.a1, L.a2, L.b, L.o, L.p));
         else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2, 16>, L.a1, L.a2, L.b, L.o, L.p));
     } else {
         if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED, 8>, L.a1, L.a2, L.b, L.o, L.p));
+        else if (L.p.epi_warps == 12) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED, 12>, L.a1, L.a2, L.b, L.o, L.p));
         else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED, 16>, L.a1, L.a2, L.b, L.o, L.p));
     }
     return 0;

@@ -121,7 +121,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
         "{\n"
         ".reg .b32 ra;\n"
         "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
         "}" ::"r"(bar),
         "r"(cta)
         : "memory");
@@ -354,6 +354,16 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
     const uint32_t swz = (uint32_t)((lane >> 1) & 3);
     const uint32_t acc_full0 = smem_u32(&ctl->acc_full[0]), acc_empty0 = smem_u32(&ctl->acc_empty[0]);
     const int i = quad * 32 + lane;              // row of the tile == TMEM lane
+    uint4 rnext[4] = {};
+    auto res_prefetch = [&](int t, int ch) {     // residual (shortcut) values of chunk `ch` of tile `t` for this thread's row
+        if (t >= p.num_tiles || ch >= nchunks) return;
+        const uint32_t r = (uint32_t)((t >> nnt_shift) * CG + (int)rank) * kTileM + (uint32_t)i;
+        if (r >= out_rows) return;
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(ep.residual) + (size_t)r * ldc +
+                                                         (t & ((1 << nnt_shift) - 1)) * BN + ch * CH);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+    };
     uint32_t tile_it = 0;
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++tile_it) {
         const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
@@ -382,15 +392,8 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
 #pragma unroll
             for (int k = 0; k < 4; ++k) up_q[k] = __shfl_sync(0xFFFFFFFFu, q00, (lane >> 2) + 8 * k);
         }
-        const __half* res_row = nullptr;
-        uint4 rnext[4] = {};
         if constexpr (kRes) {
-            res_row = reinterpret_cast<const __half*>(ep.residual) + (size_t)row * ldc + n0;
-            if (valid && hsel < nchunks) {       // first chunk's shortcut values: in flight while the main loop finishes
-                const uint4* rp = reinterpret_cast<const uint4*>(res_row + hsel * CH);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
-            }
+            if (tile_it == 0) res_prefetch(tile, hsel);      // later tiles: requested during the previous tile's last chunk
         }
         mbar_wait(acc_full0 + 8 * as, aphase);
         tc_fence_after();
@@ -406,11 +409,10 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
             if constexpr (kRes) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-                if (valid && ch + kSplit < nchunks) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res_row + (ch + kSplit) * CH);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
-                }
+                // the shortcut values of this warp's NEXT chunk - of this tile or, after the last one, of its next tile -
+                // are requested now, a whole chunk (or an accumulator wait) ahead of their use
+                if (ch + kSplit < nchunks) res_prefetch(tile, ch + kSplit);
+                else res_prefetch(tile + tile_step, hsel);
             }
             tmem_ld_wait();
             const int c = n0 + c0;

@@ -6,7 +6,5 @@ run() { # tag, env...
   env "$@" timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-sustained --layers > gpurun_out/exp_$tag.json 2> gpurun_out/exp_$tag.txt
   echo "$tag exit $? $(python -c "import json;d=json.load(open('gpurun_out/exp_$tag.json'));print(d['value'], d['breakdown_ms'])" 2>/dev/null)"
 }
-run base1 A=1
-run cg4_1 BYOLO_CG=4
-run base2 A=1
-run cg4_2 BYOLO_CG=4
+run new1 A=1
+run new2 A=1

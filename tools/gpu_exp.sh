@@ -6,5 +6,7 @@ run() { # tag, env...
   env "$@" timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-sustained --layers > gpurun_out/exp_$tag.json 2> gpurun_out/exp_$tag.txt
   echo "$tag exit $? $(python -c "import json;d=json.load(open('gpurun_out/exp_$tag.json'));print(d['value'], d['breakdown_ms'])" 2>/dev/null)"
 }
-run new1 A=1
-run new2 A=1
+run base1 A=1
+run pf1 BYOLO_L2PF=1
+run base2 A=1
+run pf2 BYOLO_L2PF=2

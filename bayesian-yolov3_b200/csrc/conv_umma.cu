@@ -904,11 +904,10 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.b_bytes = p.b_rows * swz;
     // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for a CTA pair)
     p.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((kTileM * p.cg) >> 4) << 24);
-    static const int ew_env = getenv("BYOLO_EW") ? atoi(getenv("BYOLO_EW")) : 0;
     static const int bsplit_env = getenv("BYOLO_BSPLIT") ? atoi(getenv("BYOLO_BSPLIT")) : 1;
-    // 8 epilogue warps.  16 (BYOLO_EW=16, CG = 1 only) were measured SLOWER: the block then has to fit 96 registers per
-    // thread and the staging blocks cost a pipeline stage (profiles/r01/exp_v8_switches.txt).
-    p.epi_warps = (p.cg == 1 && (ew_env == 16 || ew_env == 12)) ? ew_env : 8;
+    // 8 epilogue warps.  12 and 16 were measured: no gain / slower (16 caps the block at 96 registers per thread and the
+    // extra staging blocks cost a pipeline stage), profiles/r01/exp_v8_switches.txt.
+    p.epi_warps = 8;
     p.bsplit = bsplit_env;
     const int budget = 227 * 1024 - 1024 - (int)sizeof(SmemCtl) - p.epi_warps * kStageOutBytes - 64;
     static const int kbs_env = getenv("BYOLO_KBS") ? atoi(getenv("BYOLO_KBS")) : 0;
@@ -977,18 +976,10 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
         auto set = [](const void* f) {
             if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         };
-        set((const void*)conv_umma_kernel<1, A_TILED, 16>);
-        set((const void*)conv_umma_kernel<1, A_IM2COL, 16>);
-        set((const void*)conv_umma_kernel<1, A_STACK1, 16>);
-        set((const void*)conv_umma_kernel<1, A_STACK2, 16>);
         set((const void*)conv_umma_kernel<2, A_IM2COL, 8>);
         set((const void*)conv_umma_kernel<2, A_TILED, 8>);
         set((const void*)conv_umma_kernel<2, A_STACK1, 8>);
         set((const void*)conv_umma_kernel<2, A_STACK2, 8>);
-        set((const void*)conv_umma_kernel<1, A_TILED, 12>);
-        set((const void*)conv_umma_kernel<1, A_IM2COL, 12>);
-        set((const void*)conv_umma_kernel<1, A_STACK1, 12>);
-        set((const void*)conv_umma_kernel<1, A_STACK2, 12>);
         set((const void*)conv_umma_kernel<1, A_TILED, 8>);
         set((const void*)conv_umma_kernel<1, A_IM2COL, 8>);
         set((const void*)conv_umma_kernel<1, A_STACK1, 8>);
@@ -1020,21 +1011,13 @@ int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
         else if (L.p.amode == A_STACK2) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_STACK2, 8>, L.a1, L.a2, L.b, L.o, L.p));
         else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_TILED, 8>, L.a1, L.a2, L.b, L.o, L.p));
     } else if (L.p.amode == A_IM2COL) {
-        if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL, 8>, L.a1, L.a2, L.b, L.o, L.p));
-        else if (L.p.epi_warps == 12) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL, 12>, L.a1, L.a2, L.b, L.o, L.p));
-        else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL, 16>, L.a1, L.a2, L.b, L.o, L.p));
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL, 8>, L.a1, L.a2, L.b, L.o, L.p));
     } else if (L.p.amode == A_STACK1) {
-        if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1, 8>, L.a1, L.a2, L.b, L.o, L.p));
-        else if (L.p.epi_warps == 12) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1, 12>, L.a1, L.a2, L.b, L.o, L.p));
-        else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1, 16>, L.a1, L.a2, L.b, L.o, L.p));
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1, 8>, L.a1, L.a2, L.b, L.o, L.p));
     } else if (L.p.amode == A_STACK2) {
-        if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2, 8>, L.a1, L.a2, L.b, L.o, L.p));
-        else if (L.p.epi_warps == 12) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2, 12>, L.a1, L.a2, L.b, L.o, L.p));
-        else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2, 16>, L.a1, L.a2, L.b, L.o, L.p));
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2, 8>, L.a1, L.a2, L.b, L.o, L.p));
     } else {
-        if (L.p.epi_warps == 8) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED, 8>, L.a1, L.a2, L.b, L.o, L.p));
-        else if (L.p.epi_warps == 12) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED, 12>, L.a1, L.a2, L.b, L.o, L.p));
-        else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED, 16>, L.a1, L.a2, L.b, L.o, L.p));
+        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED, 8>, L.a1, L.a2, L.b, L.o, L.p));
     }
     return 0;
 }

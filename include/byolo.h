@@ -114,7 +114,7 @@ int byolo_get_activation(byolo_handle h, int32_t conv_index, float* dst_dev, siz
 
 /* Per-launch device timing of byolo_detect (CUDA events on the launch stream).  byolo_profile(h, 1) makes every
  * following byolo_detect record an event before each launch; byolo_profile_read returns, for the most recent one, one
- * entry per launch in order: duration [ms], kind (0 stem, 1 conv, 2 MC-stack copy, 3 decode, 4 nms), conv index (or -1)
+ * entry per launch in order: duration [ms], kind (0 stem, 1 conv, 3 decode, 4 nms; 2 is unused), conv index (or -1)
  * and that launch's algorithmic FLOPs (2*MAC), plus for conv launches the effective SM clock in MHz during the launch
  * (clock64 / globaltimer read by CTA 0; 0 elsewhere).  Returns the number of entries.  Waits for the last event. */
 int byolo_profile(byolo_handle h, int32_t enable);

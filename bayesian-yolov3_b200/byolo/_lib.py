@@ -40,6 +40,7 @@ SIGNATURES = {
     'byolo_get_activation': (C.c_int, [_P, _I, _P, _SZ, C.POINTER(_I * 4), _P]),
     'byolo_profile': (C.c_int, [_P, _I]),
     'byolo_profile_read': (C.c_int, [_P, _P, _P, _P, _P, _P, _I]),
+    'byolo_profile_read_coarse': (C.c_int, [_P, _P, _P, _P, _I]),
     'byolo_launch_count': (C.c_int, [_P, _I]),
     'byolo_flops_per_image': (C.c_double, [_P]),
 }

@@ -135,7 +135,15 @@ class Engine:
         return dst
 
     def profile(self, enable=True):
+        """False/0: off; True/1: one CUDA event before every launch; 2: coarse (stem | conv stack | decode+NMS per call)."""
         _lib.check(self.lib.byolo_profile(self.h, int(enable)))
+
+    def profile_read_coarse(self):
+        """Coarse-mode records of the most recent detect() calls (up to 256): array [n, 3] of ms (stem, conv stack, decode+NMS)."""
+        cap = 256
+        a, b, c = (np.zeros(cap, np.float32) for _ in range(3))
+        n = _lib.check(self.lib.byolo_profile_read_coarse(self.h, _np_ptr(a), _np_ptr(b), _np_ptr(c), cap))
+        return np.stack([a[:n], b[:n], c[:n]], 1)
 
     def profile_read(self):
         """Per-launch records of the last profiled detect(): list of dict(ms, kind, layer, flops)."""

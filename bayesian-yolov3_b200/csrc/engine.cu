@@ -1,6 +1,7 @@
 // libbyolo engine: weight folding/upload, per-batch execution plans (buffers, tensor maps, launch list) and the C ABI
 // declared in include/byolo.h.  The plan is this repo's replacement for the graph that
 // /root/reference/lib_yolo/yolov3.py:232-310 / 370-451 / 518-628 builds through model.ModelBuilder (model.py:20-185).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -125,7 +126,13 @@ struct Plan {
     unsigned long long* clk = nullptr;   // profiling: 4 x u64 per step (conv kernels write SM clock / global timer pairs)
     std::vector<cudaEvent_t> ev;    // profiling: steps.size() + 3 events (one before each launch, decode, nms, end)
     bool ev_recorded = false;
+    // coarse profiling (byolo_profile(h, 2)): 4 events per byolo_detect in a ring - start, after the stem launch, before the
+    // decode launch, after the NMS launch.  Nothing sits between the conv launches, so they overlap exactly as without it.
+    static constexpr int kCoarseRing = 256;
+    std::vector<cudaEvent_t> cev;
+    int coarse_n = 0;
     ~Plan() {
+        for (auto& x : cev) cudaEventDestroy(x);
         for (auto& x : ev) cudaEventDestroy(x);
         cudaFree(clk);
         for (auto& b : bufs) cudaFree(b.ptr);
@@ -145,6 +152,7 @@ struct byolo_engine {
     std::map<int, std::unique_ptr<Plan>> plans;
     Plan* last_plan = nullptr;     // plan of the most recent forward (byolo_get_activation)
     bool profiling = false;
+    bool coarse = false;           // byolo_profile(h, 2)
     // pipelined host entry (byolo_submit_host / byolo_wait_host): two slots, separate H2D and D2H copy streams
     struct HostSlot {
         float* img = nullptr; float* out = nullptr; int* cnt = nullptr;
@@ -328,8 +336,19 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
         BY_CUDA(cudaMalloc(&pl->clk, sizeof(unsigned long long) * 4 * pl->steps.size()));
         BY_CUDA(cudaMemset(pl->clk, 0, sizeof(unsigned long long) * 4 * pl->steps.size()));
     }
+    const bool coarse = e->coarse && !prof;
+    cudaEvent_t* ce = nullptr;
+    if (coarse) {
+        if (pl->cev.empty()) {
+            pl->cev.resize(4 * Plan::kCoarseRing);
+            for (auto& x : pl->cev) BY_CUDA(cudaEventCreate(&x));
+        }
+        ce = &pl->cev[4 * (pl->coarse_n % Plan::kCoarseRing)];
+        BY_CUDA(cudaEventRecord(ce[0], st));
+    }
     size_t ei = 0;
     for (Step& s : pl->steps) {
+        if (coarse && &s == &pl->steps[1]) BY_CUDA(cudaEventRecord(ce[1], st));       // the stem is the first launch
         if (prof) BY_CUDA(cudaEventRecord(pl->ev[ei++], st));
         if (s.kind == STEP_STEM) {
             const LayerWeights& w = e->weights[0];
@@ -367,6 +386,7 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
     dp.N = e->N;
     dp.D = e->D;
     if (prof) BY_CUDA(cudaEventRecord(pl->ev[ei++], st));
+    if (coarse) BY_CUDA(cudaEventRecord(ce[2], st));
     if (int r = launch_decode(dp, st)) return r;
     if (prof) { BY_CUDA(cudaEventRecord(pl->ev[ei++], st)); pl->ev_recorded = false; }
     return 0;
@@ -487,13 +507,36 @@ int byolo_detect(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed,
                            (cudaStream_t)stream))
         return r;
     if (h->profiling) { BY_CUDA(cudaEventRecord(pl->ev.back(), (cudaStream_t)stream)); pl->ev_recorded = true; }
+    if (h->coarse && !h->profiling && !pl->cev.empty()) {
+        BY_CUDA(cudaEventRecord(pl->cev[4 * (pl->coarse_n % Plan::kCoarseRing) + 3], (cudaStream_t)stream));
+        ++pl->coarse_n;
+    }
     return 0;
 }
 
 int byolo_profile(byolo_handle h, int32_t enable) {
     BY_REQUIRE(h, "null handle");
-    h->profiling = enable != 0;
+    h->profiling = enable == 1;
+    h->coarse = enable == 2;
+    if (h->coarse)
+        for (auto& kv : h->plans) kv.second->coarse_n = 0;
     return 0;
+}
+
+int byolo_profile_read_coarse(byolo_handle h, float* stem_ms, float* conv_ms, float* tail_ms, int32_t capacity) {
+    BY_REQUIRE(h && stem_ms && conv_ms && tail_ms, "null argument");
+    Plan* pl = h->last_plan;
+    BY_REQUIRE(pl && !pl->cev.empty(), "no byolo_detect has run in coarse profiling mode");
+    const int n = std::min(std::min(pl->coarse_n, (int)Plan::kCoarseRing), (int)capacity);
+    for (int i = 0; i < n; ++i) {
+        const int slot = (pl->coarse_n - n + i) % Plan::kCoarseRing;
+        cudaEvent_t* ce = &pl->cev[4 * slot];
+        BY_CUDA(cudaEventSynchronize(ce[3]));
+        BY_CUDA(cudaEventElapsedTime(&stem_ms[i], ce[0], ce[1]));
+        BY_CUDA(cudaEventElapsedTime(&conv_ms[i], ce[1], ce[2]));
+        BY_CUDA(cudaEventElapsedTime(&tail_ms[i], ce[2], ce[3]));
+    }
+    return n;
 }
 
 int byolo_profile_read(byolo_handle h, float* ms, int32_t* kind, int32_t* layer, double* flops, float* sm_mhz, int32_t capacity) {

@@ -113,11 +113,16 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
 int byolo_get_activation(byolo_handle h, int32_t conv_index, float* dst_dev, size_t capacity, int32_t shape[4], void* stream);
 
 /* Per-launch device timing of byolo_detect (CUDA events on the launch stream).  byolo_profile(h, 1) makes every
- * following byolo_detect record an event before each launch; byolo_profile_read returns, for the most recent one, one
+ * following byolo_detect record an event before each launch (mode 1); byolo_profile_read returns, for the most recent one, one
  * entry per launch in order: duration [ms], kind (0 stem, 1 conv, 3 decode, 4 nms; 2 is unused), conv index (or -1)
  * and that launch's algorithmic FLOPs (2*MAC), plus for conv launches the effective SM clock in MHz during the launch
  * (clock64 / globaltimer read by CTA 0; 0 elsewhere).  Returns the number of entries.  Waits for the last event. */
 int byolo_profile(byolo_handle h, int32_t enable);
+/* byolo_profile(h, 2): coarse mode - four events per byolo_detect (start, after the stem launch, before the decode
+ * launch, end) kept in a ring of 256 calls.  Nothing is recorded between the 74 conv launches, so they overlap
+ * (programmatic dependent launch) exactly as in an unprofiled run.  Reads the most recent calls, oldest first: duration
+ * [ms] of the stem launch, of the whole conv stack, and of decode + NMS.  Returns the number of entries. */
+int byolo_profile_read_coarse(byolo_handle h, float* stem_ms, float* conv_ms, float* tail_ms, int32_t capacity);
 int byolo_profile_read(byolo_handle h, float* ms, int32_t* kind, int32_t* layer, double* flops, float* sm_mhz, int32_t capacity);
 
 /* Number of kernels one byolo_detect launches for batch B (bench.py reports it as gpu_launches). */

@@ -48,9 +48,11 @@ def write_ecp_json(variant, out_path, boxes, img_name, img_size, model, config):
 
 
 def find_weights(config):
-    """Checkpoint lookup of the inference scripts (reference: tf.train.latest_checkpoint / '*-<step>.meta',
-    inference_epistemic.py:27-38) for BYW1 blobs named weights-<step>.byw.  config['weights'] overrides the lookup.
-    Returns (weights argument, step label)."""
+    """Checkpoint lookup of the inference scripts (reference: inference_epistemic.py:27-38, detect.py:96-105):
+    config['checkpoint_path']/config['run_id'] holds either BYW1 blobs named weights-<step>.byw or the reference's own
+    TensorFlow checkpoints (`step == 'last'`: tf.train.latest_checkpoint via the `checkpoint` state file, else the prefix
+    whose `-<step>.meta` / `-<step>.index` exists).  config['weights'] overrides the lookup.
+    Returns (weights argument for load_weights, step label); a TF checkpoint comes back as 'tf:<prefix>'."""
     if config.get('weights') is not None:
         return config['weights'], str(config.get('step', 'given'))
     folder = os.path.join(config['checkpoint_path'], config['run_id'])
@@ -58,7 +60,18 @@ def find_weights(config):
     for f in os.listdir(folder):
         if f.startswith('weights-') and f.endswith('.byw'):
             blobs[int(f[len('weights-'):-len('.byw')])] = os.path.join(folder, f)
-    assert blobs, 'no weights-<step>.byw in %s' % folder
-    step = max(blobs) if config['step'] == 'last' else int(config['step'])
-    assert step in blobs, 'could not find checkpoint'
-    return blobs[step], str(step)
+    if blobs:
+        step = max(blobs) if config['step'] == 'last' else int(config['step'])
+        assert step in blobs, 'could not find checkpoint'
+        return blobs[step], str(step)
+    from . import tf_checkpoint
+    if config['step'] == 'last':
+        prefix = tf_checkpoint.latest_checkpoint(folder)
+    else:
+        prefix = None
+        for f in sorted(os.listdir(folder)):
+            if f.endswith('-{}.meta'.format(config['step'])) or f.endswith('-{}.index'.format(config['step'])):
+                prefix = os.path.join(folder, os.path.splitext(f)[0])
+                break
+    assert prefix is not None, 'could not find checkpoint'
+    return 'tf:' + prefix, prefix.split('-')[-1]

@@ -49,11 +49,14 @@ class _Base:
             return self._weights
         w = self._config.get('weights', None)
         if w is None:
-            raise RuntimeError("no weights: set config['weights'] (layer list, BYW1 blob/path or 'synthetic:<seed>'), "
+            raise RuntimeError("no weights: set config['weights'] (layer list, BYW1 blob/path, 'tf:<checkpoint prefix>' or 'synthetic:<seed>'), "
                                "or call load_darknet53_weights / load_weights")
         if isinstance(w, str) and w.startswith('synthetic'):
             seed = int(w.split(':')[1]) if ':' in w else 0
             w = _weights.synthetic(self.variant, self.cls_cnt, seed)
+        elif isinstance(w, str) and w.startswith('tf:'):          # a TensorFlow checkpoint prefix of the reference model
+            from byolo import tf_checkpoint
+            w = tf_checkpoint.load(w[3:], self.variant, self.cls_cnt)
         elif isinstance(w, str):
             with open(os.path.expandvars(w), 'rb') as f:
                 w = f.read()

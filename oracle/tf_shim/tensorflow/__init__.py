@@ -107,16 +107,40 @@ def _t(x):
 
 
 # ------------------------------------------------------------------------------------------ scopes
+# [TF] variable_scope(None, default_name=d) makes the name unique among its siblings: d, d_1, d_2, ... (one counter per
+# parent scope and default name); an explicit name is used as it is.  Variables are recorded under their scope path the
+# way tf.layers names them (<scope>/conv2d/kernel, <scope>/batch_normalization/gamma ...), so that the reference's own
+# graph-building code tells us the checkpoint variable names (tests/golden/tf_variable_names.json).
+_UNIQ = {}
+VARIABLES = []          # (name, shape) in creation order
+
+
+def reset_names():
+    _UNIQ.clear()
+    del VARIABLES[:]
+
+
+def _record_variable(leaf, shape):
+    VARIABLES.append(('/'.join(_SCOPE + [leaf]), tuple(int(d) for d in shape)))
+
+
 @contextlib.contextmanager
 def variable_scope(name, default_name=None, **kw):
-    _SCOPE.append(name or default_name)
+    if name is None:
+        key = ('/'.join(_SCOPE), default_name)
+        n = _UNIQ.get(key, 0)
+        _UNIQ[key] = n + 1
+        name = default_name if n == 0 else '%s_%d' % (default_name, n)
+    _SCOPE.append(name)
     try:
         yield
     finally:
         _SCOPE.pop()
 
 
-name_scope = variable_scope
+@contextlib.contextmanager
+def name_scope(name, default_name=None, **kw):          # op names only: does not prefix variables
+    yield
 
 
 class _Contrib:
@@ -151,6 +175,9 @@ class layers:
         w = _PROVIDER.next_conv(kernel_size, x.shape[-1], filters, use_bias)
         k = np.asarray(w['kernel'], dtype=WORK_DTYPE)
         assert k.shape == (kernel_size, kernel_size, x.shape[-1], filters), (k.shape, kernel_size, x.shape, filters)
+        _record_variable('conv2d/kernel', k.shape)
+        if use_bias:
+            _record_variable('conv2d/bias', (filters,))
         y = _conv2d_numpy(x, k, strides, padding.upper())
         if use_bias:
             y = y + np.asarray(w['bias'], dtype=WORK_DTYPE)
@@ -161,6 +188,8 @@ class layers:
         assert not training
         w = _PROVIDER.next_bn(inputs.a.shape[-1])
         g, b, m, v = (np.asarray(w[k], dtype=WORK_DTYPE) for k in ('gamma', 'beta', 'mean', 'var'))
+        for leaf in ('gamma', 'beta', 'moving_mean', 'moving_variance'):       # creation order of tf.layers.BatchNormalization
+            _record_variable('batch_normalization/' + leaf, g.shape)
         inv = g / np.sqrt(v + WORK_DTYPE(epsilon))         # nn.batch_normalization: inv = rsqrt(var+eps)*gamma
         return Tensor(inputs.a * inv + (b - m * inv))
 

@@ -16,9 +16,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, 'oracle', 'tf_shim'))      # fake `tensorflow`, `matplotlib`
-sys.path.insert(0, '/root/reference')
-sys.path.insert(0, os.path.join(ROOT, 'bayesian-yolov3_b200'))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')                            # the reference's lib_yolo / inference_*.py win over the
+sys.path.append(os.path.join(ROOT, 'bayesian-yolov3_b200'))      # same-named shims of this repo (only `byolo` is taken from it)
+sys.path.insert(1, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 import tensorflow as tf                                          # noqa: E402  (the shim)
@@ -57,6 +57,9 @@ class Provider:
         return m
 
 
+VARIABLE_NAMES = {}
+
+
 def config_for(case):
     return {'full_img_size': list(case['img_size']), 'crop': False, 'cls_cnt': case['cls_cnt'],
             'priors': ref_yolov3.ECP_9_PRIORS, 'aleatoric_loss': True, 'inference_mode': True, 'T': case.get('T'),
@@ -75,6 +78,7 @@ def run_case(case, work_dtype=np.float32):
         rows_all, sel_all, raws_all = [], [], []
         for b in range(imgs.shape[0]):                       # the reference is batch-1 (inference_epistemic.py:193)
             tf.set_provider(Provider(weights, case['dropout_seed'], b))
+            tf.reset_names()
             model = cls(config_for(case)).init_model(inputs=tf.Tensor(imgs[b:b + 1]), training=False).get_model()
             rows = mod.concat_bbox([dl.bbox for dl in model.det_layers])
             rows_all.append(rows.a)
@@ -91,6 +95,7 @@ def run_case(case, work_dtype=np.float32):
             out['raw%d' % j] = np.stack([r[j] for r in raws_all])          # [B,T,g,g,42]
     else:
         tf.set_provider(Provider(weights, 0, 0))
+        tf.reset_names()
         model = cls(config_for(case)).init_model(inputs=tf.Tensor(imgs), training=False).get_model()
         rows = mod.concat_bbox([dl.bbox for dl in model.det_layers])
         out['rows'] = rows.a
@@ -106,6 +111,7 @@ def run_case(case, work_dtype=np.float32):
     out['dn_out'] = model.dn_out.a
     out['l36'] = model.layers[36].a[:, ::4, ::4, ::8]                      # strided samples keep the file small
     out['l61'] = model.layers[61].a[:, ::2, ::2, ::8]
+    VARIABLE_NAMES[variant] = [[n, list(sh)] for n, sh in tf.VARIABLES]      # names the reference's graph code creates
     return out
 
 
@@ -131,6 +137,10 @@ def main():
             for n in ('CITY_PERSONS_9_PRIORS', 'ECP_9_PRIORS', 'ECP_NIGHT_9_PRIORS', 'ECP_DAY_NIGHT_9_PRIORS',
                       'ECP_BIC_9_PRIORS')}
     np.savez_compressed(os.path.join(HERE, 'priors.npz'), **tabs)
+    # checkpoint variable names (scope structure from the reference's model.py / yolov3.py, uniquified the TF way)
+    import json
+    with open(os.path.join(HERE, 'tf_variable_names.json'), 'w') as f:
+        json.dump(VARIABLE_NAMES, f, indent=0)
     print('done')
 
 

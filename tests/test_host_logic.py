@@ -204,3 +204,130 @@ def test_det_maps_from_rows_follow_the_reference_dict():
     assert det['cls_entropy'][y, x, p] == row[20]
     assert np.array_equal(np.diagonal(det['epi_covar_loc'][y, x, p]), row[4:8]) and np.array_equal(det['ale_var_loc'][y, x, p], row[8:12])
     assert np.isnan(det['epi_covar_loc'][y, x, p][0, 1])
+
+
+# ------------------------------------------------------------------------------------------------ TF checkpoints (8f-1)
+def test_tf_variable_names_match_the_reference_graph_code():
+    """byolo.tf_checkpoint.variable_names vs the names recorded while the reference's own model-building code ran on
+    the TF stand-in (tests/golden/tf_variable_names.json, written by tests/golden/gen_golden.py)."""
+    import json
+    from byolo import tf_checkpoint as TC
+    ref = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'tf_variable_names.json')))
+    for variant in ('standard', 'aleatoric', 'epistemic'):
+        mine = [[n, list(sh)] for n, sh in TC.variable_names(variant, 2)]
+        assert mine == ref[variant], variant
+    names = [n for n, _ in TC.variable_names('epistemic', 2)]
+    assert 'darknet53/conv_46/conv2d/kernel' in names and 'darknet53/downsample_4/batch_normalization/moving_variance' in names
+    assert 'det_net_3/detection/conv2d/bias' in names and 'det_net_2/conv_6/conv2d/kernel' in names
+
+
+def _varint_bytes(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def _pb(field, wt, payload):
+    tag = _varint_bytes((field << 3) | wt)
+    if wt == 0:
+        return tag + _varint_bytes(payload)
+    return tag + _varint_bytes(len(payload)) + payload
+
+
+def _table_block(pairs, restart_interval=16):
+    out, restarts, last = bytearray(), [], b''
+    for i, (k, v) in enumerate(pairs):
+        shared = 0
+        if i % restart_interval == 0:
+            restarts.append(len(out))
+        else:
+            while shared < min(len(k), len(last)) and k[shared] == last[shared]:
+                shared += 1
+        out += _varint_bytes(shared) + _varint_bytes(len(k) - shared) + _varint_bytes(len(v)) + k[shared:] + v
+        last = k
+    for r in restarts or [0]:
+        out += np.uint32(r).tobytes()
+    out += np.uint32(len(restarts) or 1).tobytes()
+    return bytes(out)
+
+
+def _write_bundle(prefix, tensors, block_entries=40):
+    """Test-side writer of the tensor-bundle layout byolo.tf_checkpoint.read_bundle restates (uncompressed blocks)."""
+    data, entries = bytearray(), []
+    for name in sorted(tensors):
+        a = np.asarray(tensors[name], np.float32)          # (ascontiguousarray would turn scalars into shape (1,))
+        shape = b''.join(_pb(2, 2, _pb(1, 0, int(d))) for d in a.shape)
+        entry = _pb(1, 0, 1) + _pb(2, 2, shape) + _pb(4, 0, len(data)) + _pb(5, 0, a.nbytes)      # dtype DT_FLOAT, shard 0
+        entries.append((name.encode(), entry))
+        data += a.tobytes()
+    pairs = [(b'', _pb(1, 0, 1))] + entries                  # header: num_shards = 1 (little endian = default)
+    out, index = bytearray(), []
+    for i in range(0, len(pairs), block_entries):
+        blk = _table_block(pairs[i:i + block_entries])
+        index.append((pairs[min(i + block_entries, len(pairs)) - 1][0], _varint_bytes(len(out)) + _varint_bytes(len(blk))))
+        out += blk + b'\0' + b'\0\0\0\0'                    # no compression, crc not checked by the reader
+    meta = _table_block([])
+    meta_handle = _varint_bytes(len(out)) + _varint_bytes(len(meta))
+    out += meta + b'\0' + b'\0\0\0\0'
+    iblk = _table_block(index, restart_interval=1)
+    index_handle = _varint_bytes(len(out)) + _varint_bytes(len(iblk))
+    out += iblk + b'\0' + b'\0\0\0\0'
+    footer = meta_handle + index_handle
+    out += footer + b'\0' * (40 - len(footer)) + np.uint64(0xdb4775248b80fb57).tobytes()
+    open(prefix + '.index', 'wb').write(bytes(out))
+    open(prefix + '.data-00000-of-00001', 'wb').write(bytes(data))
+
+
+def test_tf_checkpoint_round_trip(tmp_path):
+    """weights -> variables under the reference's names -> bundle files -> read_bundle -> weights: identical; extra
+    variables (optimizer slots, global_step) are ignored; a missing variable is an error."""
+    from byolo import tf_checkpoint as TC, weights as W
+    ref = W.synthetic('aleatoric', 2, 3)
+    variables = TC.variables_from_weights('aleatoric', 2, ref)
+    # keep the files small: only variables up to 40k elements are written
+    keep = {n: a for n, a in variables.items() if a.size <= 40000}
+    keep['darknet53/conv/conv2d/kernel/Adam'] = np.zeros((3, 3, 3, 32), np.float32)       # optimizer slot
+    keep['global_step_like'] = np.array(7.0, np.float32)
+    prefix = str(tmp_path / 'model.ckpt-42')
+    _write_bundle(prefix, keep)
+    got = TC.read_bundle(prefix)
+    assert set(got) == set(keep)
+    for n in keep:
+        assert got[n].shape == np.asarray(keep[n]).shape and np.array_equal(got[n], keep[n]), n
+    with pytest.raises(KeyError):
+        TC.weights_from_variables('aleatoric', 2, got)                                    # big kernels were left out
+    full = dict(variables)
+    back = TC.weights_from_variables('aleatoric', 2, {k + ':0': v for k, v in full.items()})
+    for a, b in zip(back, ref):
+        assert set(a) == set(b) and all(np.array_equal(a[k], b[k]) for k in a)
+    (tmp_path / 'checkpoint').write_text('model_checkpoint_path: "model.ckpt-42"\n')
+    assert TC.latest_checkpoint(str(tmp_path)) == prefix
+
+
+def test_snappy_block_decoder():
+    from byolo.tf_checkpoint import _snappy_decompress
+    # literal "abcd", copy (offset 4, length 8) with a 1-byte offset tag, literal "xy"
+    src = bytes([14, (4 - 1) << 2]) + b'abcd' + bytes([((8 - 4) << 2) | 1, 4]) + bytes([(2 - 1) << 2]) + b'xy'
+    assert _snappy_decompress(src) == b'abcdabcdabcdxy'
+
+
+def test_find_weights_picks_up_reference_checkpoints(tmp_path):
+    """inference_*.py / detect.py lookup (inference_epistemic.py:27-38): BYW1 blobs first, else TF checkpoints by step."""
+    from byolo import ecp
+    run = tmp_path / 'run1'
+    run.mkdir()
+    for step in (100, 250):
+        for ext in ('.index', '.meta', '.data-00000-of-00001'):
+            (run / ('model.ckpt-%d%s' % (step, ext))).write_bytes(b'')
+    (run / 'checkpoint').write_text('model_checkpoint_path: "model.ckpt-250"\nall_model_checkpoint_paths: "model.ckpt-100"\n')
+    cfg = {'checkpoint_path': str(tmp_path), 'run_id': 'run1', 'step': 'last'}
+    assert ecp.find_weights(cfg) == ('tf:' + str(run / 'model.ckpt-250'), '250')
+    cfg['step'] = 100
+    assert ecp.find_weights(cfg) == ('tf:' + str(run / 'model.ckpt-100'), '100')
+    (run / 'weights-7.byw').write_bytes(b'x')
+    cfg['step'] = 'last'
+    assert ecp.find_weights(cfg) == (str(run / 'weights-7.byw'), '7')

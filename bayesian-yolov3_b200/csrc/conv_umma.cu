@@ -844,7 +844,7 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
         int dev_ = 0, sms_ = 148;
         if (cudaGetDevice(&dev_) == cudaSuccess) cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
         const long long m_rows = (long long)g.S * (g.H / q.stride) * (g.W / q.stride);
-        const bool pair = q.k == 3 && (q.stride == 2 || (C1 % 64 == 0 && C2 % 64 == 0));    // CTA pairs (decided below)
+        const bool pair = q.k == 3;                                                          // CTA pairs (decided below)
         const long long m_units = (m_rows + (pair ? 255 : 127)) / (pair ? 256 : 128);
         const int slots = pair ? sms_ / 2 : sms_;
         static const int bn_env = getenv("BYOLO_BN") ? atoi(getenv("BYOLO_BN")) : 0;      // 256: never narrow the tile
@@ -862,9 +862,8 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.stride = q.stride;
     // CTA pairs for the feed-bound shapes: 3x3 stride-1 convs with wide N tiles
     static const int cg_env = getenv("BYOLO_CG") ? atoi(getenv("BYOLO_CG")) : 0;     // 1 = force off, 2 = default policy
-    // (measured per layer, profiles/r01/exp_v8_switches.txt: pairs win on every 3x3 conv except the 32-channel stride-1 layer)
-    p.cg = (cg_env != 1 && q.k == 3 && p.BN >= 64 && (q.stride == 2 || (p.BN >= 128 && p.BK == 64))) ? 2 : 1;
-    if (cg_env == 3 && q.k == 3 && p.BN >= 64) p.cg = 2;      // experiment: every 3x3 conv as CTA pairs
+    // (measured per layer, profiles/r01/exp_v8_switches.txt: pairs win on every 3x3 conv, 5-23% fewer cycles)
+    p.cg = (cg_env != 1 && q.k == 3 && p.BN >= 64) ? 2 : 1;
     // 1x1 convs with K >= 1024 (the 1024 -> 512 layers): pairs halve the weight traffic (+8%); at K = 512 they lose 11%
     if (cg_env != 1 && q.k == 1 && p.BN >= 256 && p.BK == 64 && C1 + C2 >= 1024 && q.ep.out_mode == OUT_DENSE) p.cg = 2;
     if (cg_env == 4 && q.k == 1 && p.BN >= 256 && p.BK == 64 && q.ep.out_mode == OUT_DENSE) p.cg = 2;      // experiment: all wide 1x1 convs

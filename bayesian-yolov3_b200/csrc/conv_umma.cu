@@ -864,9 +864,10 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     static const int cg_env = getenv("BYOLO_CG") ? atoi(getenv("BYOLO_CG")) : 0;     // 1 = force off, 2 = default policy
     // (measured per layer, profiles/r01/exp_v8_switches.txt: pairs win on every 3x3 conv, 5-23% fewer cycles)
     p.cg = (cg_env != 1 && q.k == 3 && p.BN >= 64) ? 2 : 1;
-    // 1x1 convs with K >= 1024 (the 1024 -> 512 layers): pairs halve the weight traffic (+8%); at K = 512 they lose 11%
-    if (cg_env != 1 && q.k == 1 && p.BN >= 256 && p.BK == 64 && C1 + C2 >= 1024 && q.ep.out_mode == OUT_DENSE) p.cg = 2;
-    if (cg_env == 4 && q.k == 1 && p.BN >= 256 && p.BK == 64 && q.ep.out_mode == OUT_DENSE) p.cg = 2;      // experiment: all wide 1x1 convs
+    // wide (N tile 256) 1x1 convs: pairs halve the weight traffic per SM: -10..-12% cycles on the 512/768 -> 256 and
+    // 1024 -> 512 layers (exp_v8_switches.txt)
+    if (cg_env != 1 && q.k == 1 && p.BN >= 256 && p.BK == 64 && q.ep.out_mode == OUT_DENSE) p.cg = 2;
+    if (cg_env == 5 && q.k == 1 && p.BN >= 128 && p.BK == 64 && q.ep.out_mode == OUT_DENSE) p.cg = 2;      // experiment: N tile 128 too
     p.b_rows = p.BN / p.cg;
     static const int dbg_env = getenv("BYOLO_DBG") ? atoi(getenv("BYOLO_DBG")) : 0;
     p.dbg = dbg_env;

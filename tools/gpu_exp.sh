@@ -7,6 +7,6 @@ run() { # tag, env...
   echo "$tag exit $? $(python -c "import json;d=json.load(open('gpurun_out/exp_$tag.json'));print(d['value'], d['breakdown_ms'])" 2>/dev/null)"
 }
 run base1 A=1
-run cg3_1 BYOLO_CG=3
+run cg5_1 BYOLO_CG=5
 run base2 A=1
-run cg3_2 BYOLO_CG=3
+run cg5_2 BYOLO_CG=5

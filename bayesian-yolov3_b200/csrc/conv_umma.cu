@@ -970,21 +970,27 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     BY_CUDA(cudaGetDevice(&dev));
     BY_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     L->grid = std::min(p.num_tiles * p.cg, sms / p.cg * p.cg);
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        auto set = [](const void* f) {
-            if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        };
-        set((const void*)conv_umma_kernel<2, A_IM2COL, 8>);
-        set((const void*)conv_umma_kernel<2, A_TILED, 8>);
-        set((const void*)conv_umma_kernel<2, A_STACK1, 8>);
-        set((const void*)conv_umma_kernel<2, A_STACK2, 8>);
-        set((const void*)conv_umma_kernel<1, A_TILED, 8>);
-        set((const void*)conv_umma_kernel<1, A_IM2COL, 8>);
-        set((const void*)conv_umma_kernel<1, A_STACK1, 8>);
-        set((const void*)conv_umma_kernel<1, A_STACK2, 8>);
-    });
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute: done once for every device that is used
+    static std::mutex attr_mutex;
+    static bool attr_done[64] = {};
+    cudaError_t attr_err = cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lock(attr_mutex);
+        if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+            auto set = [&](const void* f) {
+                if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            };
+            set((const void*)conv_umma_kernel<2, A_IM2COL, 8>);
+            set((const void*)conv_umma_kernel<2, A_TILED, 8>);
+            set((const void*)conv_umma_kernel<2, A_STACK1, 8>);
+            set((const void*)conv_umma_kernel<2, A_STACK2, 8>);
+            set((const void*)conv_umma_kernel<1, A_TILED, 8>);
+            set((const void*)conv_umma_kernel<1, A_IM2COL, 8>);
+            set((const void*)conv_umma_kernel<1, A_STACK1, 8>);
+            set((const void*)conv_umma_kernel<1, A_STACK2, 8>);
+            if (attr_err == cudaSuccess && dev >= 0 && dev < 64) attr_done[dev] = true;
+        }
+    }
     BY_CUDA(attr_err);
     return 0;
 }

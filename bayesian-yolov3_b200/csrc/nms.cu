@@ -24,6 +24,7 @@
 // are split across the cluster and exchanged through distributed shared memory (two cluster barriers per batch).
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 #include <cooperative_groups.h>
 
@@ -342,24 +343,321 @@ nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float 
     if (CS > 1) cluster.sync();                            // nobody leaves while a peer may still touch its shared memory
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Chunked variant for N > 32768 candidates per image (e.g. the reference's own ECP geometry, 1024 x 1920: N = 120960).
+// The candidates cannot all be sorted in shared memory, so the greedy scan walks the global (score desc, index asc) order
+// in CHUNKS of at most 4096 candidates: a radix select over the 64-bit composite (score key : ~index) finds a lower bound
+// below the previous chunk such that at most 4096 candidates fall in between (one histogram pass over the scores per
+// level, 15 bits per level; the first level almost always suffices), the chunk is compacted, sorted and scanned exactly
+// like a sorted prefix in nms_kernel, and the kept list persists across chunks.  Stops at max_out kept or when every
+// candidate has been visited, so the result is the exact greedy selection for any N and any number of score ties.
+// ----------------------------------------------------------------------------------------------------------------------
+constexpr int kSelBits = 15;
+constexpr int kSelBins = 1 << kSelBits;
+constexpr size_t kChunkScratchOff = (size_t)kTopK * 4;                                           // after key_hi
+constexpr size_t kChunkScratchBytes = (sizeof(Box4) + 4) * kBatch + 4u * (kBatch * kWords + 9 * kWords);
+constexpr size_t kChunkRegionA = (size_t)kSelBins * 4;                                           // histogram | key_hi + scan scratch
+static_assert(kChunkScratchOff + kChunkScratchBytes <= kChunkRegionA, "scan scratch must fit beside the keys");
+constexpr size_t kChunkSmem = kChunkRegionA + (size_t)kTopK * 4 + (sizeof(Box4) + 4 + 4) * kMaxOut;
+
+__device__ __forceinline__ unsigned long long composite(uint32_t key, uint32_t idx) {      // larger = earlier in selection order
+    return ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+
+__device__ void bitonic_sort32(uint32_t* key_hi, uint32_t* key_lo, int NP) {
+    const int tid = threadIdx.x;
+    for (int k = 2; k <= NP; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int pidx = tid; pidx < (NP >> 1); pidx += kNmsThreads) {
+                const int i = ((pidx & ~(j - 1)) << 1) | (pidx & (j - 1));
+                const int l = i | j;
+                const uint32_t hi_i = key_hi[i], hi_l = key_hi[l];
+                const uint32_t lo_i = key_lo[i], lo_l = key_lo[l];
+                const bool i_first = (hi_i > hi_l) || (hi_i == hi_l && lo_i < lo_l);
+                const bool up = (i & k) == 0;
+                if (i_first != up) {
+                    key_hi[i] = hi_l; key_hi[l] = hi_i;
+                    key_lo[i] = lo_l; key_lo[l] = lo_i;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int CS>
+__global__ void __launch_bounds__(kNmsThreads, 1)
+nms_chunked_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float thr, int max_out,
+                   float* __restrict__ out_rows, int* __restrict__ out_idx, int* __restrict__ out_count) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = CS > 1 ? (int)cluster.block_rank() : 0;
+    const int img = blockIdx.x / CS;
+    const float* rows = rows_all + (size_t)img * N * D;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sm);                                   // [kSelBins]
+    uint32_t* key_hi = reinterpret_cast<uint32_t*>(sm);                                 // [kTopK] (after the selection)
+    uint8_t* aux = sm + kChunkScratchOff;
+    Box4* cand = reinterpret_cast<Box4*>(aux);                                          // [kBatch]
+    float* cand_area = reinterpret_cast<float*>(cand + kBatch);                         // [kBatch]
+    uint32_t* mask = reinterpret_cast<uint32_t*>(cand_area + kBatch);                   // [kBatch][kWords]
+    uint32_t* dead = mask + kBatch * kWords;
+    uint32_t* contested = dead + kWords;
+    uint32_t* has_row = contested + kWords;
+    uint32_t* selw = has_row + kWords;                                                  // [2 * kWords]
+    uint32_t* dpart = selw + 2 * kWords;                                                // [kWords]
+    uint32_t* key_lo = reinterpret_cast<uint32_t*>(sm + kChunkRegionA);                 // [kTopK] candidate indices of the chunk
+    Box4* kept = reinterpret_cast<Box4*>(key_lo + kTopK);                               // [kMaxOut]  persists across chunks
+    float* kept_area = reinterpret_cast<float*>(kept + kMaxOut);                        // [kMaxOut]
+    int* kept_idx = reinterpret_cast<int*>(kept_area + kMaxOut);                        // [kMaxOut]
+    __shared__ int s_kept, s_fill, s_bin, s_above;
+    __shared__ int s_warp_sum[32];
+
+    if (tid == 0) s_kept = 0;
+    unsigned long long upper = ~0ull;          // exclusive: candidates with composite >= upper have been visited
+    bool upper_open = true;                    // nothing visited yet (even composite ~0 would be eligible)
+    int visited = 0;
+    __syncthreads();
+
+    while (visited < N && s_kept < max_out) {
+        // ---- radix select: lower = largest bound such that #{lower <= c < upper} <= kTopK and >= 1 --------------------
+        unsigned long long prefix = 0ull;      // digits fixed so far (high bits), all lower bits zero
+        int fixed_bits = 0;
+        unsigned long long lower = 0ull;
+        while (true) {
+            const int shift = max(64 - fixed_bits - kSelBits, 0);
+            const int digit_bits = min(kSelBits, 64 - fixed_bits);
+            for (int i = tid; i < kSelBins; i += kNmsThreads) hist[i] = 0u;
+            __syncthreads();
+            for (int i = tid; i < N; i += kNmsThreads) {
+                const unsigned long long c = composite(ordered_key(rows[(size_t)i * D + obj_idx]), (uint32_t)i);
+                const bool below = upper_open || c < upper;
+                const bool match = fixed_bits == 0 || (c >> (64 - fixed_bits)) == (prefix >> (64 - fixed_bits));
+                if (below && match) atomicAdd(&hist[(uint32_t)(c >> shift) & ((1u << digit_bits) - 1u)], 1u);
+            }
+            __syncthreads();
+            // thread t owns bins [32t, 32t+32); suffix sums from the top bin downwards
+            constexpr int per = kSelBins / kNmsThreads;
+            int local = 0;
+            for (int b = 0; b < per; ++b) local += (int)hist[tid * per + b];
+            int incl = local;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_down_sync(0xFFFFFFFFu, incl, o);
+                if (lane + o < 32) incl += v;
+            }
+            if (lane == 0) s_warp_sum[warp] = incl;
+            if (tid == 0) { s_bin = -1; s_above = 0; }
+            __syncthreads();
+            int above = 0;
+            for (int w = warp + 1; w < 32; ++w) above += s_warp_sum[w];
+            const int above_me = above + incl - local;                 // matching candidates in bins above my range
+            // the crossing bin: the first bin (from the top) whose inclusive count exceeds kTopK, or - if the total fits -
+            // "below the lowest bin" (s_bin stays -1)
+            if (above_me <= kTopK && above_me + local > kTopK) {
+                int cum = above_me;
+                for (int b = per - 1; b >= 0; --b) {
+                    const int h = (int)hist[tid * per + b];
+                    if (cum + h > kTopK) { s_bin = tid * per + b; s_above = cum; break; }
+                    cum += h;
+                }
+            }
+            __syncthreads();
+            const int bin = s_bin, above_bin = s_above;
+            if (bin < 0) {                     // everything that matches fits in one chunk
+                lower = prefix;                // (prefix has zeros below the fixed digits: the smallest composite with this prefix)
+                break;
+            }
+            if (above_bin >= 1) {              // take the bins above the crossing bin; the crossing bin waits for the next chunk
+                lower = prefix | ((unsigned long long)(bin + 1) << shift);
+                break;
+            }
+            // the top remaining bin alone exceeds kTopK: fix its digit and look at the next digit inside it
+            prefix |= (unsigned long long)bin << shift;
+            fixed_bits += digit_bits;
+            __syncthreads();
+        }
+
+        // ---- compaction of the chunk, sort ------------------------------------------------------------------------------
+        __syncthreads();
+        for (int i = tid; i < kTopK; i += kNmsThreads) { key_hi[i] = 0u; key_lo[i] = 0xFFFFFFFFu; }
+        if (tid == 0) s_fill = 0;
+        __syncthreads();
+        for (int i = tid; i < N; i += kNmsThreads) {
+            const uint32_t key = ordered_key(rows[(size_t)i * D + obj_idx]);
+            const unsigned long long c = composite(key, (uint32_t)i);
+            if ((upper_open || c < upper) && c >= lower) {
+                const int pos = atomicAdd(&s_fill, 1);
+                key_hi[pos] = key;
+                key_lo[pos] = (uint32_t)i;
+            }
+        }
+        __syncthreads();
+        const int n_cand = s_fill;             // 1 .. kTopK by construction of `lower`
+        bitonic_sort32(key_hi, key_lo, kTopK);
+
+        // ---- batched greedy scan over the chunk (same phases as nms_kernel) ---------------------------------------------
+        for (int base = 0; base < n_cand; base += kBatch) {
+            const int kept_before = s_kept;
+            if (kept_before >= max_out) break;
+            const int nb = min(kBatch, n_cand - base);
+            if (tid < kBatch) {
+                Box4 b;
+                float a = -1.f;
+                b.ymin = b.xmin = __int_as_float(0x7f800000);
+                b.ymax = b.xmax = __int_as_float(0xff800000);
+                if (tid < nb) load_box(rows + (size_t)key_lo[base + tid] * D, &b, &a);
+                cand[tid] = b;
+                cand_area[tid] = a;
+            }
+            if (tid < kWords) { dead[tid] = 0u; contested[tid] = 0u; has_row[tid] = 0u; dpart[tid] = 0u; }
+            if (CS > 1)
+                for (int i = tid; i < kBatch * kWords; i += kNmsThreads) mask[i] = 0u;
+            __syncthreads();
+            {
+                const int c = tid & (kBatch - 1), part = crank * 2 + (tid >> 9);
+                const int chunk = (kept_before + 2 * CS - 1) / (2 * CS);
+                const int j0 = part * chunk, j1 = min(kept_before, j0 + chunk);
+                const Box4 me = cand[c];
+                const float my_area = cand_area[c];
+                bool hit = false;
+                if (c < nb)
+                    for (int j = j0; j < j1; ++j)
+                        if (iou_gt(me, my_area, kept[j], kept_area[j], thr)) { hit = true; break; }
+                if (hit || c >= nb) atomicOr(&dpart[c >> 5], 1u << (c & 31));
+            }
+            __syncthreads();
+            if (CS > 1) {
+                cluster.sync();
+                if (tid < kWords * CS) atomicOr(&dead[tid & (kWords - 1)], cluster.map_shared_rank(dpart, tid / kWords)[tid & (kWords - 1)]);
+            } else if (tid < kWords) {
+                dead[tid] = dpart[tid];
+            }
+            __syncthreads();
+            {
+                uint32_t* mask_to = mask;
+                uint32_t* contested_to = contested;
+                uint32_t* has_row_to = has_row;
+                if (CS > 1 && lane < CS) {
+                    mask_to = cluster.map_shared_rank(mask, lane);
+                    contested_to = cluster.map_shared_rank(contested, lane);
+                    has_row_to = cluster.map_shared_rank(has_row, lane);
+                }
+                const bool writer = CS > 1 ? (lane < CS) : (lane == 0);
+                for (int it = 0, k = warp; k < kBatch; k += kNmsThreads / 32, ++it) {
+                    if (CS > 1 && (it % CS) != crank) continue;
+                    const bool k_alive = !((dead[k >> 5] >> (k & 31)) & 1u);
+                    const int w0 = k >> 5;
+                    if (CS == 1 && (lane < w0 || !k_alive)) mask[k * kWords + (lane & (kWords - 1))] = 0u;
+                    if (!k_alive) continue;
+                    const Box4 bk = cand[k];
+                    const float ak = cand_area[k];
+                    uint32_t any = 0u;
+                    for (int w = w0; w < kWords; ++w) {
+                        const int c = w * 32 + lane;
+                        const bool bit = (c > k) && !((dead[w] >> lane) & 1u) && iou_gt(cand[c], cand_area[c], bk, ak, thr);
+                        const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
+                        if (writer && (CS == 1 || word)) mask_to[k * kWords + w] = word;
+                        any |= word;
+                        if (word && writer) atomicOr(&contested_to[w], word);
+                    }
+                    if (any && writer) atomicOr(&has_row_to[k >> 5], 1u << (k & 31));
+                }
+            }
+            if (CS > 1) cluster.sync(); else __syncthreads();
+            if (warp == 0) {
+                const uint32_t alive = (lane < kWords) ? ~dead[lane] : 0u;
+                uint32_t walk = (lane < kWords) ? (alive & (contested[lane] | has_row[lane])) : 0u;
+                uint32_t sel = alive & ~walk;
+                uint32_t removed = 0u;
+                while (true) {
+                    const uint32_t cur = walk & ~removed;
+                    const uint32_t vote = __ballot_sync(0xFFFFFFFFu, cur != 0u);
+                    if (!vote) break;
+                    const int src = __ffs(vote) - 1;
+                    const uint32_t wv = __shfl_sync(0xFFFFFFFFu, cur, src);
+                    const int bit = __ffs(wv) - 1;
+                    const int k = src * 32 + bit;
+                    if (lane < kWords) removed |= mask[k * kWords + lane];
+                    if (lane == src) { walk &= ~(1u << bit); sel |= 1u << bit; }
+                }
+                int cnt = __popc(sel), pre = cnt;
+                for (int o = 1; o < kWords; o <<= 1) {
+                    const int v = __shfl_up_sync(0xFFFFFFFFu, pre, o);
+                    if (lane >= o) pre += v;
+                }
+                const int before = pre - cnt;
+                const int room = max_out - kept_before;
+                if (lane < kWords) {
+                    uint32_t keepw = sel;
+                    if (before >= room) keepw = 0u;
+                    else if (before + cnt > room) {
+                        int need = room - before;
+                        uint32_t t = sel, out = 0u;
+                        while (need-- > 0) { const uint32_t low = t & (0u - t); out |= low; t ^= low; }
+                        keepw = out;
+                    }
+                    selw[lane] = keepw;
+                    selw[kWords + lane] = (uint32_t)min(before, room);
+                }
+                const int total = __shfl_sync(0xFFFFFFFFu, pre, kWords - 1);
+                if (lane == 0) s_kept = kept_before + min(total, room);
+            }
+            __syncthreads();
+            if (tid < kBatch) {
+                const uint32_t wsel = selw[tid >> 5];
+                if ((wsel >> (tid & 31)) & 1u) {
+                    const int pos = kept_before + (int)selw[kWords + (tid >> 5)] + __popc(wsel & ((1u << (tid & 31)) - 1u));
+                    kept[pos] = cand[tid];
+                    kept_area[pos] = cand_area[tid];
+                    kept_idx[pos] = (int)key_lo[base + tid];
+                }
+            }
+            __syncthreads();
+        }
+        visited += n_cand;
+        upper = lower;
+        upper_open = false;
+        __syncthreads();
+    }
+
+    const int n_kept = s_kept;
+    float* orow = out_rows + (size_t)img * max_out * D;
+    for (int e = crank * kNmsThreads + tid; e < max_out * D; e += kNmsThreads * CS) {
+        const int k = e / D, c = e - k * D;
+        orow[e] = (k < n_kept) ? rows[(size_t)kept_idx[k] * D + c] : 0.f;
+    }
+    if (out_idx && crank == 0)
+        for (int k = tid; k < max_out; k += kNmsThreads) out_idx[(size_t)img * max_out + k] = (k < n_kept) ? kept_idx[k] : -1;
+    if (tid == 0 && crank == 0 && out_count) out_count[img] = n_kept;
+    if (CS > 1) cluster.sync();
+}
+
 size_t nms_workspace_bytes(int, int) { return 0; }
 
 int launch_nms(const float* rows, int B, int N, int D, int obj_idx, float iou_thr, int max_out, float* out_rows, int* out_idx,
                int* out_count, void*, size_t, cudaStream_t st) {
-    BY_REQUIRE(N >= 0 && N <= kMaxN, "NMS kernel handles up to 32768 candidates per image");
+    BY_REQUIRE(N >= 0 && (long long)N * D < (1ll << 31), "NMS: candidate rows must be 32-bit indexable");
     BY_REQUIRE(max_out >= 1 && max_out <= kMaxOut, "max_out must be in [1, 2048]");
     BY_REQUIRE(iou_thr >= 0.f, "iou_thr must be >= 0");
     BY_REQUIRE(obj_idx >= 4 && obj_idx < D, "obj_idx out of range");
     if (B == 0) return 0;
+    const bool chunked = N > kMaxN || (getenv("BYOLO_NMS_CHUNKED") && atoi(getenv("BYOLO_NMS_CHUNKED")) == 1);      // tests force it on small N
     int NP = 2;
     while (NP < N) NP <<= 1;
     const size_t region0 = std::max({(size_t)NP * 4, kAuxBytes, N > 4096 ? (size_t)65536 * 2 : (size_t)0});
-    const size_t smem = region0 + (size_t)NP * 2;
+    const size_t smem = chunked ? kChunkSmem : region0 + (size_t)NP * 2;
     BY_REQUIRE(smem <= 227 * 1024 - 1024, "NMS shared memory budget exceeded");
     // cluster size: as many CTAs per image as keep all images resident at once (148 SMs, one CTA per SM)
     const int cs_env = getenv("BYOLO_NMS_CS") ? atoi(getenv("BYOLO_NMS_CS")) : 0;      // tests force every cluster size
-    static int max_clusters[4] = {-1, -1, -1, -1};          // co-resident clusters of size 1 << i at this smem size (queried once)
-    static size_t queried_smem = 0;
+    // co-resident clusters of size 1 << i at this smem size: queried once per (device, smem size); the query also opts
+    // the kernels in to the large dynamic shared memory on that device
+    static std::mutex occ_mutex;
+    static int occ_cache[2][64][4];
+    static size_t occ_smem[2][64] = {};
+    int dev = 0;
+    BY_CUDA(cudaGetDevice(&dev));
+    BY_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+    int max_clusters[4];
     auto launch = [&](auto kernel, int cs) -> cudaError_t {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(B * cs);
@@ -374,6 +672,21 @@ int launch_nms(const float* rows, int B, int N, int D, int obj_idx, float iou_th
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, kernel, rows, N, D, obj_idx, iou_thr, max_out, NP, region0, out_rows, out_idx, out_count);
+    };
+    auto launch_chunked = [&](auto kernel, int cs) -> cudaError_t {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(B * cs);
+        cfg.blockDim = dim3(kNmsThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, rows, N, D, obj_idx, iou_thr, max_out, out_rows, out_idx, out_count);
     };
     auto occupancy = [&](auto kernel, int cs) -> int {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess) return 0;
@@ -392,19 +705,36 @@ int launch_nms(const float* rows, int B, int N, int D, int obj_idx, float iou_th
         if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
         return n;
     };
-    if (queried_smem != smem) {
-        max_clusters[0] = occupancy(nms_kernel<1>, 1);
-        max_clusters[1] = occupancy(nms_kernel<2>, 2);
-        max_clusters[2] = occupancy(nms_kernel<4>, 4);
-        max_clusters[3] = occupancy(nms_kernel<8>, 8);
-        queried_smem = smem;
+    {
+        std::lock_guard<std::mutex> lock(occ_mutex);
+        const int v = chunked ? 1 : 0;
+        if (occ_smem[v][dev] != smem) {
+            if (chunked) {
+                occ_cache[v][dev][0] = occupancy(nms_chunked_kernel<1>, 1);
+                occ_cache[v][dev][1] = occupancy(nms_chunked_kernel<2>, 2);
+                occ_cache[v][dev][2] = occupancy(nms_chunked_kernel<4>, 4);
+                occ_cache[v][dev][3] = occupancy(nms_chunked_kernel<8>, 8);
+            } else {
+                occ_cache[v][dev][0] = occupancy(nms_kernel<1>, 1);
+                occ_cache[v][dev][1] = occupancy(nms_kernel<2>, 2);
+                occ_cache[v][dev][2] = occupancy(nms_kernel<4>, 4);
+                occ_cache[v][dev][3] = occupancy(nms_kernel<8>, 8);
+            }
+            occ_smem[v][dev] = smem;
+        }
+        for (int i = 0; i < 4; ++i) max_clusters[i] = occ_cache[v][dev][i];
     }
     int cs = 1;
     for (int i = 3; i >= 1; --i)
         if (max_clusters[i] >= B) { cs = 1 << i; break; }
     if (cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8) cs = cs_env;
     cudaError_t err;
-    if (cs == 8) err = launch(nms_kernel<8>, 8);
+    if (chunked) {
+        if (cs == 8) err = launch_chunked(nms_chunked_kernel<8>, 8);
+        else if (cs == 4) err = launch_chunked(nms_chunked_kernel<4>, 4);
+        else if (cs == 2) err = launch_chunked(nms_chunked_kernel<2>, 2);
+        else err = launch_chunked(nms_chunked_kernel<1>, 1);
+    } else if (cs == 8) err = launch(nms_kernel<8>, 8);
     else if (cs == 4) err = launch(nms_kernel<4>, 4);
     else if (cs == 2) err = launch(nms_kernel<2>, 2);
     else err = launch(nms_kernel<1>, 1);

@@ -104,6 +104,66 @@ def test_nms_stress_full_size_bit_exact(cluster, monkeypatch):
     assert cnt.min() == 1000                                    # generator guarantees >= 1000 survivors
 
 
+def _random_rows(B, N, D, obj_idx, seed, tie_frac=0.05):
+    rng = np.random.default_rng(seed)
+    rows = rng.random((B, N, D), dtype=np.float32)
+    cy, cx = rng.random((B, N), dtype=np.float32), rng.random((B, N), dtype=np.float32)
+    h, w = (0.02 + 0.1 * rng.random((B, N))).astype(np.float32), (0.01 + 0.05 * rng.random((B, N))).astype(np.float32)
+    rows[..., 0], rows[..., 1], rows[..., 2], rows[..., 3] = cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2
+    score = (1.0 / (1.0 + np.exp(-rng.normal(-3.0, 2.0, (B, N))))).astype(np.float32)
+    n_tie = int(N * tie_frac)
+    for b in range(B):                                           # exact score ties -> index order decides
+        src, dst = rng.integers(0, N, n_tie), rng.integers(0, N, n_tie)
+        score[b, dst] = score[b, src]
+    rows[..., obj_idx] = score
+    return rows
+
+
+@pytest.mark.parametrize('cluster', [1, 8])
+def test_nms_chunked_kernel_on_stress_rows(cluster, monkeypatch):
+    """The chunked kernel (score-ordered chunks of <= 4096 candidates, used for N > 32768) forced onto the 22743-row stress
+    case: same selection as the oracle."""
+    monkeypatch.setenv('BYOLO_NMS_CHUNKED', '1')
+    monkeypatch.setenv('BYOLO_NMS_CS', str(cluster))
+    rows = stress_rows(2, 106)
+    boxes, cnt, idx = _nms_gpu(rows, 14)
+    for b in range(rows.shape[0]):
+        want = ONMS.nms(rows[b], 14)
+        assert cnt[b] == len(want) and np.array_equal(idx[b, :cnt[b]], want), 'image %d' % b
+        assert np.array_equal(boxes[b, :cnt[b]], rows[b][want])
+
+
+def test_nms_beyond_32768_candidates():
+    """N = 120960 = the reference's ECP geometry (1024 x 1920, inference_epistemic.py:213-233), D = 23."""
+    rows = _random_rows(2, 120960, 23, 14, 11)
+    boxes, cnt, idx = _nms_gpu(rows, 14)
+    for b in range(rows.shape[0]):
+        want = ONMS.nms(rows[b], 14)
+        assert cnt[b] == len(want) == 1000 and np.array_equal(idx[b, :cnt[b]], want), 'image %d' % b
+        assert np.array_equal(boxes[b, :cnt[b]], rows[b][want])
+
+
+def _tie_rows():
+    """10000 candidates share ONE score and only 500 distinct boxes (the radix select has to descend into the index bits and
+    three chunks are visited for ~500 survivors), then 6000 candidates with another single score and small distinct boxes."""
+    rows = _random_rows(1, 16000, 7, 4, 12, tie_frac=0.0)
+    rows[0, :, 2] = rows[0, :, 0] + 0.004
+    rows[0, :, 3] = rows[0, :, 1] + 0.004
+    rows[0, :10000, :4] = rows[0, np.arange(10000) % 500, :4]
+    rows[0, :10000, 4] = 0.75
+    rows[0, 10000:, 4] = 0.5
+    return rows
+
+
+def test_nms_chunked_with_more_ties_than_a_chunk(monkeypatch):
+    monkeypatch.setenv('BYOLO_NMS_CHUNKED', '1')
+    rows = _tie_rows()
+    boxes, cnt, idx = _nms_gpu(rows, 4, max_out=2000)
+    want = ONMS.nms(rows[0], 4, 2000)
+    assert cnt[0] == len(want) == 2000 and np.array_equal(idx[0, :cnt[0]], want)
+    assert 0 < (want < 10000).sum() <= 500 and (want >= 10000).sum() >= 1500
+
+
 @pytest.mark.parametrize('cluster', [1, 8])
 def test_nms_edge_cases(cluster, monkeypatch):
     monkeypatch.setenv('BYOLO_NMS_CS', str(cluster))

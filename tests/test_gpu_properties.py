@@ -103,3 +103,19 @@ def test_detect_output_structure_608():
         iou = inter / (area[:, None] + area[None] - inter + 1e-30)
         np.fill_diagonal(iou, 0)
         assert iou.max() <= 0.5 + 1e-6
+
+
+def test_detect_on_a_wide_frame_with_more_than_32768_anchors():
+    """608 x 1216 (non-square, N = 45486 > 32768): the whole path runs and the chunked NMS picks exactly what the oracle
+    picks from the engine's own rows.  (The reference's ECP geometry, 1024 x 1920, has N = 120960: covered for the NMS
+    alone in test_gpu_parity.py::test_nms_beyond_32768_candidates.)"""
+    import byolo
+    from oracle import nms as ONMS
+    eng = byolo.Engine('epistemic', (608, 1216), 2, T=2, max_batch=1, precision='fp16').load_weights(W.synthetic('epistemic', 2, 0))
+    img = torch.from_numpy(np.random.default_rng(5).random((1, 608, 1216, 3), dtype=np.float32)).cuda()
+    boxes, cnt, idx, rows = eng.detect(img, seed=3, want_rows=True)
+    torch.cuda.synchronize()
+    rows, cnt, idx = rows.cpu().numpy(), cnt.cpu().numpy(), idx.cpu().numpy()
+    assert rows.shape == (1, 45486, 23)
+    want = ONMS.nms(rows[0], 14)
+    assert cnt[0] == len(want) and np.array_equal(idx[0, :cnt[0]], want)

@@ -103,6 +103,162 @@ __device__ void bitonic_sort(uint32_t* key_hi, uint16_t* key_lo, int NP) {
     }
 }
 
+// The scan phase shared by both kernels: the n_cand candidates listed in key_lo[] (selection-priority order) are walked in
+// batches of 512 against the kept list, which grows in place.  All CTAs of a cluster call it with identical state.
+struct ScanBuf {
+    Box4* cand;            // [kBatch]
+    float* cand_area;      // [kBatch]
+    uint32_t* mask;        // [kBatch][kWords] row k: later candidates k suppresses
+    uint32_t* dead;        // [kWords] suppressed by kept boxes of earlier batches / padding
+    uint32_t* contested;   // [kWords] has a potential suppressor inside the batch
+    uint32_t* has_row;     // [kWords] suppresses somebody inside the batch
+    uint32_t* selw;        // [2 * kWords] final selection of the batch + rank offsets
+    uint32_t* dpart;       // [kWords] phase (A) hits found by THIS CTA
+    Box4* kept;            // [max_out]
+    float* kept_area;      // [max_out]
+    int* kept_idx;         // [max_out]
+};
+
+template <int CS, typename IdxT>
+__device__ __forceinline__ void scan_candidates(const float* __restrict__ rows, int D, const IdxT* key_lo, int n_cand, float thr,
+                                                int max_out, const ScanBuf& sb, int* s_kept, cg::cluster_group& cluster, int crank) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Box4* cand = sb.cand;
+    float* cand_area = sb.cand_area;
+    uint32_t* mask = sb.mask;
+    uint32_t* dead = sb.dead;
+    uint32_t* contested = sb.contested;
+    uint32_t* has_row = sb.has_row;
+    uint32_t* selw = sb.selw;
+    uint32_t* dpart = sb.dpart;
+    Box4* kept = sb.kept;
+    float* kept_area = sb.kept_area;
+    int* kept_idx = sb.kept_idx;
+    for (int base = 0; base < n_cand; base += kBatch) {
+        const int kept_before = (*s_kept);
+        if (kept_before >= max_out) break;
+        const int nb = min(kBatch, n_cand - base);
+        if (tid < kBatch) {
+            Box4 b;
+            float a = -1.f;
+            b.ymin = b.xmin = __int_as_float(0x7f800000);
+            b.ymax = b.xmax = __int_as_float(0xff800000);
+            if (tid < nb) load_box(rows + (size_t)key_lo[base + tid] * D, &b, &a);
+            cand[tid] = b;
+            cand_area[tid] = a;
+        }
+        if (tid < kWords) { dead[tid] = 0u; contested[tid] = 0u; has_row[tid] = 0u; dpart[tid] = 0u; }
+        if (CS > 1)                                    // peers only deliver the non-zero words of the bit matrix
+            for (int i = tid; i < kBatch * kWords; i += kNmsThreads) mask[i] = 0u;
+        __syncthreads();
+        {   // (A) two threads per candidate and CTA, each scanning one of the 2*CS parts of the kept list
+            const int c = tid & (kBatch - 1), part = crank * 2 + (tid >> 9);
+            const int chunk = (kept_before + 2 * CS - 1) / (2 * CS);
+            const int j0 = part * chunk, j1 = min(kept_before, j0 + chunk);
+            const Box4 me = cand[c];
+            const float my_area = cand_area[c];
+            bool hit = false;
+            if (c < nb)
+                for (int j = j0; j < j1; ++j)
+                    if (iou_gt(me, my_area, kept[j], kept_area[j], thr)) { hit = true; break; }
+            if (hit || c >= nb) atomicOr(&dpart[c >> 5], 1u << (c & 31));
+        }
+        __syncthreads();
+        if (CS > 1) {
+            cluster.sync();                            // every CTA's hits are in its dpart[]; all masks are zeroed
+            if (tid < kWords * CS) atomicOr(&dead[tid & (kWords - 1)], cluster.map_shared_rank(dpart, tid / kWords)[tid & (kWords - 1)]);
+        } else if (tid < kWords) {
+            dead[tid] = dpart[tid];
+        }
+        __syncthreads();
+        // (B) suppression matrix, one ballot per 32 pairs: row k, word w, lane l <-> candidate c = 32w + l.  The rows
+        // are dealt round-robin to the CTAs of the cluster; a CTA delivers its non-zero words to every CTA.
+        {
+            uint32_t* mask_to = mask;
+            uint32_t* contested_to = contested;
+            uint32_t* has_row_to = has_row;
+            if (CS > 1 && lane < CS) {                 // lane l of every warp writes to CTA l
+                mask_to = cluster.map_shared_rank(mask, lane);
+                contested_to = cluster.map_shared_rank(contested, lane);
+                has_row_to = cluster.map_shared_rank(has_row, lane);
+            }
+            const bool writer = CS > 1 ? (lane < CS) : (lane == 0);
+            for (int it = 0, k = warp; k < kBatch; k += kNmsThreads / 32, ++it) {
+                if (CS > 1 && (it % CS) != crank) continue;              // warp-uniform
+                const bool k_alive = !((dead[k >> 5] >> (k & 31)) & 1u);
+                const int w0 = k >> 5;
+                if (CS == 1 && (lane < w0 || !k_alive)) mask[k * kWords + (lane & (kWords - 1))] = 0u;
+                if (!k_alive) continue;                                  // warp-uniform
+                const Box4 bk = cand[k];
+                const float ak = cand_area[k];
+                uint32_t any = 0u;
+                for (int w = w0; w < kWords; ++w) {
+                    const int c = w * 32 + lane;
+                    const bool bit = (c > k) && !((dead[w] >> lane) & 1u) && iou_gt(cand[c], cand_area[c], bk, ak, thr);
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
+                    if (writer && (CS == 1 || word)) mask_to[k * kWords + w] = word;
+                    any |= word;
+                    if (word && writer) atomicOr(&contested_to[w], word);
+                }
+                if (any && writer) atomicOr(&has_row_to[k >> 5], 1u << (k & 31));
+            }
+        }
+        if (CS > 1) cluster.sync(); else __syncthreads();
+        // (C) resolve.  A candidate that nobody in the batch can suppress and that suppresses nobody is kept without
+        // looking at the order; only the others (bit in `contested` or `has_row`) go through the sequential walk.
+        if (warp == 0) {
+            const uint32_t alive = (lane < kWords) ? ~dead[lane] : 0u;
+            uint32_t walk = (lane < kWords) ? (alive & (contested[lane] | has_row[lane])) : 0u;
+            uint32_t sel = alive & ~walk;
+            uint32_t removed = 0u;
+            while (true) {
+                const uint32_t cur = walk & ~removed;
+                const uint32_t vote = __ballot_sync(0xFFFFFFFFu, cur != 0u);
+                if (!vote) break;
+                const int src = __ffs(vote) - 1;
+                const uint32_t wv = __shfl_sync(0xFFFFFFFFu, cur, src);
+                const int bit = __ffs(wv) - 1;
+                const int k = src * 32 + bit;
+                if (lane < kWords) removed |= mask[k * kWords + lane];
+                if (lane == src) { walk &= ~(1u << bit); sel |= 1u << bit; }
+            }
+            // cap at max_out in selection order: prefix counts over the 16 words
+            int cnt = __popc(sel), pre = cnt;
+            for (int o = 1; o < kWords; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, pre, o);
+                if (lane >= o) pre += v;
+            }
+            const int before = pre - cnt;                            // selected in lower words
+            const int room = max_out - kept_before;
+            if (lane < kWords) {
+                uint32_t keepw = sel;
+                if (before >= room) keepw = 0u;
+                else if (before + cnt > room) {                      // keep only the first (room - before) set bits
+                    int need = room - before;
+                    uint32_t t = sel, out = 0u;
+                    while (need-- > 0) { const uint32_t low = t & (0u - t); out |= low; t ^= low; }
+                    keepw = out;
+                }
+                selw[lane] = keepw;
+                selw[kWords + lane] = (uint32_t)min(before, room);  // rank offset of this word
+            }
+            const int total = __shfl_sync(0xFFFFFFFFu, pre, kWords - 1);
+            if (lane == 0) (*s_kept) = kept_before + min(total, room);
+        }
+        __syncthreads();
+        if (tid < kBatch) {                                          // append in order, in parallel
+            const uint32_t wsel = selw[tid >> 5];
+            if ((wsel >> (tid & 31)) & 1u) {
+                const int pos = kept_before + (int)selw[kWords + (tid >> 5)] + __popc(wsel & ((1u << (tid & 31)) - 1u));
+                kept[pos] = cand[tid];
+                kept_area[pos] = cand_area[tid];
+                kept_idx[pos] = (int)key_lo[base + tid];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <int CS>
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float thr, int max_out, int NP,
@@ -201,128 +357,9 @@ nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float 
         bitonic_sort(key_hi, key_lo, NPs);
 
         // ---- 2. batched greedy scan ----
-        for (int base = 0; base < n_cand; base += kBatch) {
-            const int kept_before = s_kept;
-            if (kept_before >= max_out) break;
-            const int nb = min(kBatch, n_cand - base);
-            if (tid < kBatch) {
-                Box4 b;
-                float a = -1.f;
-                b.ymin = b.xmin = __int_as_float(0x7f800000);
-                b.ymax = b.xmax = __int_as_float(0xff800000);
-                if (tid < nb) load_box(rows + (size_t)key_lo[base + tid] * D, &b, &a);
-                cand[tid] = b;
-                cand_area[tid] = a;
-            }
-            if (tid < kWords) { dead[tid] = 0u; contested[tid] = 0u; has_row[tid] = 0u; dpart[tid] = 0u; }
-            if (CS > 1)                                    // peers only deliver the non-zero words of the bit matrix
-                for (int i = tid; i < kBatch * kWords; i += kNmsThreads) mask[i] = 0u;
-            __syncthreads();
-            {   // (A) two threads per candidate and CTA, each scanning one of the 2*CS parts of the kept list
-                const int c = tid & (kBatch - 1), part = crank * 2 + (tid >> 9);
-                const int chunk = (kept_before + 2 * CS - 1) / (2 * CS);
-                const int j0 = part * chunk, j1 = min(kept_before, j0 + chunk);
-                const Box4 me = cand[c];
-                const float my_area = cand_area[c];
-                bool hit = false;
-                if (c < nb)
-                    for (int j = j0; j < j1; ++j)
-                        if (iou_gt(me, my_area, kept[j], kept_area[j], thr)) { hit = true; break; }
-                if (hit || c >= nb) atomicOr(&dpart[c >> 5], 1u << (c & 31));
-            }
-            __syncthreads();
-            if (CS > 1) {
-                cluster.sync();                            // every CTA's hits are in its dpart[]; all masks are zeroed
-                if (tid < kWords * CS) atomicOr(&dead[tid & (kWords - 1)], cluster.map_shared_rank(dpart, tid / kWords)[tid & (kWords - 1)]);
-            } else if (tid < kWords) {
-                dead[tid] = dpart[tid];
-            }
-            __syncthreads();
-            // (B) suppression matrix, one ballot per 32 pairs: row k, word w, lane l <-> candidate c = 32w + l.  The rows
-            // are dealt round-robin to the CTAs of the cluster; a CTA delivers its non-zero words to every CTA.
-            {
-                uint32_t* mask_to = mask;
-                uint32_t* contested_to = contested;
-                uint32_t* has_row_to = has_row;
-                if (CS > 1 && lane < CS) {                 // lane l of every warp writes to CTA l
-                    mask_to = cluster.map_shared_rank(mask, lane);
-                    contested_to = cluster.map_shared_rank(contested, lane);
-                    has_row_to = cluster.map_shared_rank(has_row, lane);
-                }
-                const bool writer = CS > 1 ? (lane < CS) : (lane == 0);
-                for (int it = 0, k = warp; k < kBatch; k += kNmsThreads / 32, ++it) {
-                    if (CS > 1 && (it % CS) != crank) continue;              // warp-uniform
-                    const bool k_alive = !((dead[k >> 5] >> (k & 31)) & 1u);
-                    const int w0 = k >> 5;
-                    if (CS == 1 && (lane < w0 || !k_alive)) mask[k * kWords + (lane & (kWords - 1))] = 0u;
-                    if (!k_alive) continue;                                  // warp-uniform
-                    const Box4 bk = cand[k];
-                    const float ak = cand_area[k];
-                    uint32_t any = 0u;
-                    for (int w = w0; w < kWords; ++w) {
-                        const int c = w * 32 + lane;
-                        const bool bit = (c > k) && !((dead[w] >> lane) & 1u) && iou_gt(cand[c], cand_area[c], bk, ak, thr);
-                        const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
-                        if (writer && (CS == 1 || word)) mask_to[k * kWords + w] = word;
-                        any |= word;
-                        if (word && writer) atomicOr(&contested_to[w], word);
-                    }
-                    if (any && writer) atomicOr(&has_row_to[k >> 5], 1u << (k & 31));
-                }
-            }
-            if (CS > 1) cluster.sync(); else __syncthreads();
-            // (C) resolve.  A candidate that nobody in the batch can suppress and that suppresses nobody is kept without
-            // looking at the order; only the others (bit in `contested` or `has_row`) go through the sequential walk.
-            if (warp == 0) {
-                const uint32_t alive = (lane < kWords) ? ~dead[lane] : 0u;
-                uint32_t walk = (lane < kWords) ? (alive & (contested[lane] | has_row[lane])) : 0u;
-                uint32_t sel = alive & ~walk;
-                uint32_t removed = 0u;
-                while (true) {
-                    const uint32_t cur = walk & ~removed;
-                    const uint32_t vote = __ballot_sync(0xFFFFFFFFu, cur != 0u);
-                    if (!vote) break;
-                    const int src = __ffs(vote) - 1;
-                    const uint32_t wv = __shfl_sync(0xFFFFFFFFu, cur, src);
-                    const int bit = __ffs(wv) - 1;
-                    const int k = src * 32 + bit;
-                    if (lane < kWords) removed |= mask[k * kWords + lane];
-                    if (lane == src) { walk &= ~(1u << bit); sel |= 1u << bit; }
-                }
-                // cap at max_out in selection order: prefix counts over the 16 words
-                int cnt = __popc(sel), pre = cnt;
-                for (int o = 1; o < kWords; o <<= 1) {
-                    const int v = __shfl_up_sync(0xFFFFFFFFu, pre, o);
-                    if (lane >= o) pre += v;
-                }
-                const int before = pre - cnt;                            // selected in lower words
-                const int room = max_out - kept_before;
-                if (lane < kWords) {
-                    uint32_t keepw = sel;
-                    if (before >= room) keepw = 0u;
-                    else if (before + cnt > room) {                      // keep only the first (room - before) set bits
-                        int need = room - before;
-                        uint32_t t = sel, out = 0u;
-                        while (need-- > 0) { const uint32_t low = t & (0u - t); out |= low; t ^= low; }
-                        keepw = out;
-                    }
-                    selw[lane] = keepw;
-                    selw[kWords + lane] = (uint32_t)min(before, room);  // rank offset of this word
-                }
-                const int total = __shfl_sync(0xFFFFFFFFu, pre, kWords - 1);
-                if (lane == 0) s_kept = kept_before + min(total, room);
-            }
-            __syncthreads();
-            if (tid < kBatch) {                                          // append in order, in parallel
-                const uint32_t wsel = selw[tid >> 5];
-                if ((wsel >> (tid & 31)) & 1u) {
-                    const int pos = kept_before + (int)selw[kWords + (tid >> 5)] + __popc(wsel & ((1u << (tid & 31)) - 1u));
-                    kept[pos] = cand[tid];
-                    kept_area[pos] = cand_area[tid];
-                    kept_idx[pos] = key_lo[base + tid];
-                }
-            }
-            __syncthreads();
+        {
+            const ScanBuf sb{cand, cand_area, mask, dead, contested, has_row, selw, dpart, kept, kept_area, kept_idx};
+            scan_candidates<CS, uint16_t>(rows, D, key_lo, n_cand, thr, max_out, sb, &s_kept, cluster, crank);
         }
         // the cut was sufficient iff the cap was reached or nothing was left below it
         if (full || s_kept >= max_out || n_cand == N) break;
@@ -495,124 +532,10 @@ nms_chunked_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx
         const int n_cand = s_fill;             // 1 .. kTopK by construction of `lower`
         bitonic_sort32(key_hi, key_lo, kTopK);
 
-        // ---- batched greedy scan over the chunk (same phases as nms_kernel) ---------------------------------------------
-        for (int base = 0; base < n_cand; base += kBatch) {
-            const int kept_before = s_kept;
-            if (kept_before >= max_out) break;
-            const int nb = min(kBatch, n_cand - base);
-            if (tid < kBatch) {
-                Box4 b;
-                float a = -1.f;
-                b.ymin = b.xmin = __int_as_float(0x7f800000);
-                b.ymax = b.xmax = __int_as_float(0xff800000);
-                if (tid < nb) load_box(rows + (size_t)key_lo[base + tid] * D, &b, &a);
-                cand[tid] = b;
-                cand_area[tid] = a;
-            }
-            if (tid < kWords) { dead[tid] = 0u; contested[tid] = 0u; has_row[tid] = 0u; dpart[tid] = 0u; }
-            if (CS > 1)
-                for (int i = tid; i < kBatch * kWords; i += kNmsThreads) mask[i] = 0u;
-            __syncthreads();
-            {
-                const int c = tid & (kBatch - 1), part = crank * 2 + (tid >> 9);
-                const int chunk = (kept_before + 2 * CS - 1) / (2 * CS);
-                const int j0 = part * chunk, j1 = min(kept_before, j0 + chunk);
-                const Box4 me = cand[c];
-                const float my_area = cand_area[c];
-                bool hit = false;
-                if (c < nb)
-                    for (int j = j0; j < j1; ++j)
-                        if (iou_gt(me, my_area, kept[j], kept_area[j], thr)) { hit = true; break; }
-                if (hit || c >= nb) atomicOr(&dpart[c >> 5], 1u << (c & 31));
-            }
-            __syncthreads();
-            if (CS > 1) {
-                cluster.sync();
-                if (tid < kWords * CS) atomicOr(&dead[tid & (kWords - 1)], cluster.map_shared_rank(dpart, tid / kWords)[tid & (kWords - 1)]);
-            } else if (tid < kWords) {
-                dead[tid] = dpart[tid];
-            }
-            __syncthreads();
-            {
-                uint32_t* mask_to = mask;
-                uint32_t* contested_to = contested;
-                uint32_t* has_row_to = has_row;
-                if (CS > 1 && lane < CS) {
-                    mask_to = cluster.map_shared_rank(mask, lane);
-                    contested_to = cluster.map_shared_rank(contested, lane);
-                    has_row_to = cluster.map_shared_rank(has_row, lane);
-                }
-                const bool writer = CS > 1 ? (lane < CS) : (lane == 0);
-                for (int it = 0, k = warp; k < kBatch; k += kNmsThreads / 32, ++it) {
-                    if (CS > 1 && (it % CS) != crank) continue;
-                    const bool k_alive = !((dead[k >> 5] >> (k & 31)) & 1u);
-                    const int w0 = k >> 5;
-                    if (CS == 1 && (lane < w0 || !k_alive)) mask[k * kWords + (lane & (kWords - 1))] = 0u;
-                    if (!k_alive) continue;
-                    const Box4 bk = cand[k];
-                    const float ak = cand_area[k];
-                    uint32_t any = 0u;
-                    for (int w = w0; w < kWords; ++w) {
-                        const int c = w * 32 + lane;
-                        const bool bit = (c > k) && !((dead[w] >> lane) & 1u) && iou_gt(cand[c], cand_area[c], bk, ak, thr);
-                        const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
-                        if (writer && (CS == 1 || word)) mask_to[k * kWords + w] = word;
-                        any |= word;
-                        if (word && writer) atomicOr(&contested_to[w], word);
-                    }
-                    if (any && writer) atomicOr(&has_row_to[k >> 5], 1u << (k & 31));
-                }
-            }
-            if (CS > 1) cluster.sync(); else __syncthreads();
-            if (warp == 0) {
-                const uint32_t alive = (lane < kWords) ? ~dead[lane] : 0u;
-                uint32_t walk = (lane < kWords) ? (alive & (contested[lane] | has_row[lane])) : 0u;
-                uint32_t sel = alive & ~walk;
-                uint32_t removed = 0u;
-                while (true) {
-                    const uint32_t cur = walk & ~removed;
-                    const uint32_t vote = __ballot_sync(0xFFFFFFFFu, cur != 0u);
-                    if (!vote) break;
-                    const int src = __ffs(vote) - 1;
-                    const uint32_t wv = __shfl_sync(0xFFFFFFFFu, cur, src);
-                    const int bit = __ffs(wv) - 1;
-                    const int k = src * 32 + bit;
-                    if (lane < kWords) removed |= mask[k * kWords + lane];
-                    if (lane == src) { walk &= ~(1u << bit); sel |= 1u << bit; }
-                }
-                int cnt = __popc(sel), pre = cnt;
-                for (int o = 1; o < kWords; o <<= 1) {
-                    const int v = __shfl_up_sync(0xFFFFFFFFu, pre, o);
-                    if (lane >= o) pre += v;
-                }
-                const int before = pre - cnt;
-                const int room = max_out - kept_before;
-                if (lane < kWords) {
-                    uint32_t keepw = sel;
-                    if (before >= room) keepw = 0u;
-                    else if (before + cnt > room) {
-                        int need = room - before;
-                        uint32_t t = sel, out = 0u;
-                        while (need-- > 0) { const uint32_t low = t & (0u - t); out |= low; t ^= low; }
-                        keepw = out;
-                    }
-                    selw[lane] = keepw;
-                    selw[kWords + lane] = (uint32_t)min(before, room);
-                }
-                const int total = __shfl_sync(0xFFFFFFFFu, pre, kWords - 1);
-                if (lane == 0) s_kept = kept_before + min(total, room);
-            }
-            __syncthreads();
-            if (tid < kBatch) {
-                const uint32_t wsel = selw[tid >> 5];
-                if ((wsel >> (tid & 31)) & 1u) {
-                    const int pos = kept_before + (int)selw[kWords + (tid >> 5)] + __popc(wsel & ((1u << (tid & 31)) - 1u));
-                    kept[pos] = cand[tid];
-                    kept_area[pos] = cand_area[tid];
-                    kept_idx[pos] = (int)key_lo[base + tid];
-                }
-            }
-            __syncthreads();
+        // ---- batched greedy scan over the chunk (same code as nms_kernel) ------------------------------------------------
+        {
+            const ScanBuf sb{cand, cand_area, mask, dead, contested, has_row, selw, dpart, kept, kept_area, kept_idx};
+            scan_candidates<CS, uint32_t>(rows, D, key_lo, n_cand, thr, max_out, sb, &s_kept, cluster, crank);
         }
         visited += n_cand;
         upper = lower;

@@ -119,3 +119,28 @@ def test_detect_on_a_wide_frame_with_more_than_32768_anchors():
     assert rows.shape == (1, 45486, 23)
     want = ONMS.nms(rows[0], 14)
     assert cnt[0] == len(want) and np.array_equal(idx[0, :cnt[0]], want)
+
+
+def test_reference_main_configuration_ecp_1024x1920_T50():
+    """The configuration inference_epistemic.main() ships with (inference_epistemic.py:212-233): one 1024 x 1920 frame,
+    T = 50 MC samples, cls_cnt 2 -> 120960 anchors through the chunked NMS.  Checks structure, determinism and that the
+    selection equals the oracle's on the engine's own rows; prints the time per frame."""
+    import byolo
+    from oracle import nms as ONMS
+    eng = byolo.Engine('epistemic', (1024, 1920), 2, T=50, max_batch=1, precision='fp16').load_weights(W.synthetic('epistemic', 2, 0))
+    img = torch.from_numpy(np.random.default_rng(9).random((1, 1024, 1920, 3), dtype=np.float32)).cuda()
+    boxes, cnt, idx, rows = eng.detect(img, seed=5, want_rows=True)
+    boxes2, cnt2, idx2 = eng.detect(img, seed=5)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(3):
+        eng.detect(img, seed=5)
+    t1.record()
+    torch.cuda.synchronize()
+    print('ECP frame 1024x1920, T=50: %.2f ms per frame' % (t0.elapsed_time(t1) / 3))
+    rows, cnt_h, idx_h = rows.cpu().numpy(), cnt.cpu().numpy(), idx.cpu().numpy()
+    assert rows.shape == (1, 120960, 23) and boxes.shape == (1, 1000, 23)
+    assert torch.equal(idx, idx2) and torch.equal(torch.nan_to_num(boxes), torch.nan_to_num(boxes2))
+    want = ONMS.nms(rows[0], 14)
+    assert cnt_h[0] == len(want) and np.array_equal(idx_h[0, :cnt_h[0]], want)

@@ -331,3 +331,19 @@ def test_find_weights_picks_up_reference_checkpoints(tmp_path):
     (run / 'weights-7.byw').write_bytes(b'x')
     cfg['step'] = 'last'
     assert ecp.find_weights(cfg) == (str(run / 'weights-7.byw'), '7')
+
+
+def test_bench_reference_arm_prints_one_json_record():
+    """bench.py --impl reference: exactly one stdout line, a JSON record with the contract's keys (the driver parses it)."""
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1'],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    rec = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert k in rec, k
+    assert rec['impl'] == 'reference' and rec['value'] > 0 and rec['cpu_baseline']['kind'] == 'port' and rec['cpu_baseline']['cores'] >= 1
+    assert rec['e2e']['h2d_bytes_per_step'] == 0 and 'workload' in rec['config'] and 'model' not in rec['config']

@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B runs of library switches; alternate the variants so that thermal drift does not favour one of them.
+# A/B runs of library switches (BYOLO_CG, BYOLO_KBS, BYOLO_BN, BYOLO_BSPLIT, BYOLO_NMS_CS ...); alternate the variants so
+# that thermal drift does not favour one of them, and compare per-layer cycles (ms x MHz) rather than ms.
 mkdir -p gpurun_out
 run() { # tag, env...
   local tag=$1; shift
@@ -7,6 +8,6 @@ run() { # tag, env...
   echo "$tag exit $? $(python -c "import json;d=json.load(open('gpurun_out/exp_$tag.json'));print(d['value'], d['breakdown_ms'])" 2>/dev/null)"
 }
 run base1 A=1
-run cg5_1 BYOLO_CG=5
+run var1 BYOLO_CG=1
 run base2 A=1
-run cg5_2 BYOLO_CG=5
+run var2 BYOLO_CG=1

@@ -117,3 +117,65 @@ def test_nms_ties_and_degenerate_boxes():
     assert np.array_equal(a, b) and 10 in a
     assert len(ONMS.nms(rows[:0], 4)) == 0
     assert len(ONMS.nms(rows, 4, max_out=7)) == 7
+
+
+# ------------------------------------------------------------------------------------------------ independent pins
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors of the Random123 distribution (kat_vectors: counter, key -> output)."""
+    from oracle import philox
+    kat = [((0x00000000,) * 4, (0x00000000, 0x00000000), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox.philox4x32_10(*[np.array([c], np.uint32) for c in ctr], key[0], key[1])
+        assert tuple(int(g[0]) for g in got) == want, (ctr, key)
+
+
+def test_dropout_stream_statistics():
+    """keep rate 0.9 (threshold 6554/65536), independent across MC samples, layers and images."""
+    from oracle import philox
+    shape = (38, 38, 256)
+    m = [philox.keep_mask(1003, 4, t, 0, shape, 0.1) for t in range(4)]
+    n = m[0].size
+    for x in m:
+        assert abs(x.mean() - (1 - 6554 / 65536)) < 4 * np.sqrt(0.09 / n)
+    for a in range(4):
+        for b in range(a + 1, 4):                      # P(both kept) = 0.81 if independent
+            assert abs((m[a] & m[b]).mean() - 0.81) < 5e-3
+    other_layer = philox.keep_mask(1003, 5, 0, 0, shape, 0.1)
+    other_image = philox.keep_mask(1003, 4, 0, 1, shape, 0.1)
+    other_seed = philox.keep_mask(1004, 4, 0, 0, shape, 0.1)
+    for x in (other_layer, other_image, other_seed):
+        assert abs((m[0] & x).mean() - 0.81) < 5e-3 and not np.array_equal(m[0], x)
+    assert np.array_equal(m[0], philox.keep_mask(1003, 4, 0, 0, shape, 0.1))          # and reproducible
+
+
+def test_nms_oracle_agrees_with_torchvision_on_tie_free_inputs():
+    """torchvision.ops.nms implements the same greedy rule (suppress iff IoU > thr); on inputs without score ties and
+    without degenerate boxes the kept index sequences must coincide (SURVEY.md 8c-iii sanity check)."""
+    import torch
+    import torchvision
+    rng = np.random.default_rng(21)
+    n = 3000
+    cy, cx = rng.random(n), rng.random(n)
+    h, w = 0.02 + 0.1 * rng.random(n), 0.02 + 0.1 * rng.random(n)
+    rows = np.zeros((n, 7), np.float32)
+    rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3] = cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2
+    rows[:, 4] = rng.permutation(n).astype(np.float32) / n                            # distinct scores
+    mine = ONMS.nms(rows, 4, 1000)
+    xyxy = torch.from_numpy(rows[:, [1, 0, 3, 2]].copy())
+    theirs = torchvision.ops.nms(xyxy, torch.from_numpy(rows[:, 4].copy()), 0.5)[:1000].numpy()
+    agree = np.mean(mine[:len(theirs)] == theirs[:len(mine)])
+    assert len(mine) == len(theirs) and agree > 0.995, (len(mine), len(theirs), agree)   # fp rounding of IoU near 0.5 may flip a pair
+
+
+def test_epistemic_determinant_column_against_float64():
+    """Column 12 of the epistemic row is det(cov) (layers.py:488): the oracle's fp32 value against a float64 evaluation of
+    the same raw samples, bounded relative to prod(diag) (the scale of a 4x4 PSD determinant)."""
+    rng = np.random.default_rng(5)
+    raw = (rng.standard_normal((6, 3, 4, 42)) * 0.7).astype(np.float32)              # T = 6 samples of one 3x4 map
+    rows32 = D.decode_epistemic(raw, PRI[1], 1, 2, np.float32)
+    rows64 = D.decode_epistemic(raw.astype(np.float64), PRI[1], 1, 2, np.float64)
+    scale = np.prod(np.abs(rows64[:, 4:8]), -1)
+    assert np.all(np.abs(rows32[:, 12] - rows64[:, 12]) <= 1e-3 * scale + 1e-12)
+    assert np.allclose(rows32[:, 4:8], rows64[:, 4:8], rtol=1e-3, atol=1e-6)          # the diagonal itself

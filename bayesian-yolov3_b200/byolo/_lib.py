@@ -8,8 +8,8 @@ LIB_PATH = os.path.join(HERE, 'libbyolo.so')
 
 STANDARD, ALEATORIC, EPISTEMIC = 0, 1, 2
 VARIANT_ID = {'standard': STANDARD, 'aleatoric': ALEATORIC, 'epistemic': EPISTEMIC}
-PREC_FP32, PREC_FP16_SIMT, PREC_FP16 = 0, 1, 2
-PRECISION_ID = {'fp32': PREC_FP32, 'fp16-simt': PREC_FP16_SIMT, 'fp16': PREC_FP16}
+PREC_FP32, PREC_FP16_SIMT, PREC_FP16, PREC_FP16X3 = 0, 1, 2, 3
+PRECISION_ID = {'fp32': PREC_FP32, 'fp16-simt': PREC_FP16_SIMT, 'fp16': PREC_FP16, 'fp16x3': PREC_FP16X3}
 
 
 class Config(C.Structure):
@@ -19,7 +19,7 @@ class Config(C.Structure):
                 ('prior_h', C.c_float * 9), ('prior_w', C.c_float * 9)]
 
 
-# name -> (restype, argtypes); must list every symbol include/byolo.h declares (tests/test_abi.py checks)
+# name -> (restype, argtypes); must list every symbol include/byolo.h declares (tests/test_host_logic.py checks)
 _P, _I, _U64, _F, _SZ = C.c_void_p, C.c_int32, C.c_uint64, C.c_float, C.c_size_t
 SIGNATURES = {
     'byolo_version': (C.c_int, []),
@@ -30,13 +30,15 @@ SIGNATURES = {
     'byolo_output_shape': (C.c_int, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     'byolo_forward': (C.c_int, [_P, _P, _I, _U64, _I, _P, _P]),
     'byolo_nms': (C.c_int, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P]),
+    'byolo_nms_ex': (C.c_int, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _I, _I, _I, _P]),
+    'byolo_detect_packed': (C.c_int, [_P, _P, _I, _U64, _I, _F, _I, _P, _P, _P]),
     'byolo_detect': (C.c_int, [_P, _P, _I, _U64, _I, _F, _I, _P, _P, _P, _P, _P]),
     'byolo_detect_host': (C.c_int, [_P, _P, _I, _U64, _I, _F, _I, _P, _P, _P]),
     'byolo_submit_host': (C.c_int, [_P, _P, _I, _U64, _I, _F, _I, _P, _P, _I, _P]),
     'byolo_wait_host': (C.c_int, [_P, _I]),
     'byolo_decode': (C.c_int, [_P, _P, _P, _P, _I, _P, _P]),
     'byolo_conv_layer': (C.c_int, [_I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _U64, _I, _F,
-                                   _P, _P]),
+                                   _I, _I, _P, _P]),
     'byolo_get_activation': (C.c_int, [_P, _I, _P, _SZ, C.POINTER(_I * 4), _P]),
     'byolo_profile': (C.c_int, [_P, _I]),
     'byolo_profile_read': (C.c_int, [_P, _P, _P, _P, _P, _P, _I]),

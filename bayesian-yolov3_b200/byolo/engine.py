@@ -90,6 +90,17 @@ class Engine:
                                          _ptr(boxes), _ptr(idx), _ptr(cnt), _stream()))
         return (boxes, cnt, idx, rows) if want_rows else (boxes, cnt, idx)
 
+    def detect_packed(self, img, seed=0, image_index0=0, max_out=1000, iou_thr=0.5, out=None):
+        """detect() writing ONE fp32 block [B,max_out+1,D]: rows in selection order, zero padded, and in row max_out
+        (count, 0, ...) - the message of the multi-GPU all-gather (byolo.dist)."""
+        B = self._check_img(img)
+        if out is None:
+            out = torch.empty((B, max_out + 1, self.D), dtype=torch.float32, device=img.device)
+        assert out.is_cuda and out.is_contiguous() and tuple(out.shape) == (B, max_out + 1, self.D)
+        _lib.check(self.lib.byolo_detect_packed(self.h, _ptr(img), B, seed, image_index0, iou_thr, max_out, _ptr(out), None,
+                                                _stream()))
+        return out
+
     def detect_host(self, img_host, seed=0, image_index0=0, max_out=1000, iou_thr=0.5, out=None):
         """Host numpy/pinned-tensor images in, host numpy results out (copies + sync inside): the sess.run analogue."""
         a = img_host.numpy() if isinstance(img_host, torch.Tensor) else np.ascontiguousarray(img_host, np.float32)
@@ -162,24 +173,27 @@ class Engine:
         return float(self.lib.byolo_flops_per_image(self.h))
 
 
-def nms(rows, obj_idx, max_out=1000, iou_thr=0.5):
-    """rows [B,N,D] fp32 cuda -> (boxes [B,max_out,D], count [B], idx [B,max_out])."""
+def nms(rows, obj_idx, max_out=1000, iou_thr=0.5, packed=False, cluster=0, chunked=False):
+    """rows [B,N,D] fp32 cuda -> (boxes [B,max_out,D], count [B], idx [B,max_out]);
+    packed=True -> (packed [B,max_out+1,D] whose last row is (count, 0, ...), idx).  cluster / chunked: test hooks."""
     assert rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous() and rows.dim() == 3
     B, N, D = rows.shape
-    boxes = torch.empty((B, max_out, D), dtype=torch.float32, device=rows.device)
+    boxes = torch.empty((B, max_out + int(packed), D), dtype=torch.float32, device=rows.device)
     idx = torch.empty((B, max_out), dtype=torch.int32, device=rows.device)
-    cnt = torch.zeros((B,), dtype=torch.int32, device=rows.device)
+    cnt = None if packed else torch.empty((B,), dtype=torch.int32, device=rows.device)
     with torch.cuda.device(rows.device):
-        _lib.check(_lib.lib().byolo_nms(_ptr(rows), B, N, D, obj_idx, iou_thr, max_out, _ptr(boxes), _ptr(idx), _ptr(cnt),
-                                        _stream()))
-    return boxes, cnt, idx
+        _lib.check(_lib.lib().byolo_nms_ex(_ptr(rows), B, N, D, obj_idx, iou_thr, max_out, _ptr(boxes), _ptr(idx), _ptr(cnt),
+                                           int(packed), cluster, int(chunked), _stream()))
+    return (boxes, idx) if packed else (boxes, cnt, idx)
 
 
 def conv_layer(x, kernel, bn=None, bias=None, x2=None, residual=None, stride=1, upsample=False, precision='fp16',
-               dropout_layer=-1, T=1, seed=0, image_index0=0, drop_prob=0.1):
+               dropout_layer=-1, T=1, seed=0, image_index0=0, drop_prob=0.1, t1=1, t2=1):
     """Per-layer test hook (byolo_conv_layer): x [S,H,W,C1] (+ x2 [S,H,W,C2]) dense fp32 cuda; kernel HWIO numpy;
-    bn = dict(beta,gamma,mean,var) or bias array.  Returns dense fp32 [S,Ho,Wo,cout] (x2 size if upsample)."""
+    bn = dict(beta,gamma,mean,var) or bias array.  Returns dense fp32 [S,Ho,Wo,cout] (x2 size if upsample).
+    t1 / t2 > 1: x (alone) / x2 holds S/t samples that the conv reads as S MC-stacked samples (stack_feature_map)."""
     S, H, W, c1 = x.shape
+    S *= t1
     c2 = x2.shape[3] if x2 is not None else 0
     k = kernel.shape[0]
     cout = kernel.shape[3]
@@ -194,5 +208,5 @@ def conv_layer(x, kernel, bn=None, bias=None, x2=None, residual=None, stride=1, 
             _lib.PRECISION_ID[precision], _ptr(x.contiguous()), _ptr(x2.contiguous() if x2 is not None else None), S, H, W,
             c1, c2, k, stride, cout, _np_ptr(kern), _np_ptr(bn_a), _np_ptr(bias_a),
             _ptr(residual.contiguous() if residual is not None else None), int(upsample), dropout_layer, T, seed,
-            image_index0, drop_prob, _ptr(out), _stream()))
+            image_index0, drop_prob, t1, t2, _ptr(out), _stream()))
     return out

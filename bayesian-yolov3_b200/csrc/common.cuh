@@ -111,6 +111,7 @@ struct ConvProblem {
     int cout_pad;            // rows of the weight matrix (multiple of 16)
     const __half* w16;       // [cout_pad, K] K-major, K = k*k*(C1+C2) ordered (tap, channel); BN scale folded
     const float* w32;        // [K, cout_pad] fp32, same folding (CUDA-core path)
+    int x3;                  // split-fp16 mode (BYOLO_PREC_FP16X3): activations [rows][hi C | lo C], w16 = [2 cout_pad, K] (hi rows, lo rows)
     Epilogue ep;
 };
 
@@ -118,10 +119,12 @@ int launch_conv_umma(const ConvProblem& p, cudaStream_t st);                 // 
 int launch_conv_simt(const ConvProblem& p, bool act_half, cudaStream_t st);  // conv_simt.cu
 int launch_stem(const float* img, int B, int H, int W, const float* w32 /*[27,32]*/, const float* bias,
                 void* out, bool act_half, cudaStream_t st);                  // conv_simt.cu
-int launch_stem_mma(const float* img, int B, int H, int W, const __half* w16 /*[32,27]*/, const float* bias, void* out,
-                    cudaStream_t st);                                        // stem.cu (fp16 operands, mma.sync)
-int launch_pack(const float* dense, void* padded, Geom g, bool act_half, cudaStream_t st);
-int launch_unpack(const void* padded, float* dense, Geom g, bool act_half, cudaStream_t st);
+int launch_stem_mma(const float* img, int B, int H, int W, const __half* w16 /*[32 (x2: hi, lo)][27]*/, const float* bias, void* out,
+                    bool x3, cudaStream_t st);                               // stem.cu (fp16 operands, mma.sync)
+// activation storage formats: fp32 | fp16 | split fp16 (pixel = [hi C halves | lo C halves], value = hi + lo)
+enum ActFmt : int { ACT_F32 = 0, ACT_F16 = 1, ACT_F16_HILO = 2 };
+int launch_pack(const float* dense, void* act, Geom g, int act_fmt, cudaStream_t st);
+int launch_unpack(const void* act, float* dense, Geom g, int act_fmt, cudaStream_t st);
 
 struct DecodeProblem {
     int variant;             // 0 standard, 1 aleatoric, 2 epistemic
@@ -137,8 +140,12 @@ struct DecodeProblem {
 };
 int launch_decode(const DecodeProblem& p, cudaStream_t st);                  // decode.cu
 
+struct NmsOptions {
+    int packed = 0;          // 1: out_rows is [B, max_out + 1, D]; row max_out of every image = (count, 0, ...)
+    int force_cs = 0;        // test hook: cluster size 1 | 2 | 4 | 8 instead of the occupancy-based choice
+    int force_chunked = 0;   // test hook: take the N > 32768 path for any N
+};
 int launch_nms(const float* rows, int B, int N, int D, int obj_idx, float iou_thr, int max_out, float* out_rows,
-               int* out_idx, int* out_count, void* workspace, size_t workspace_bytes, cudaStream_t st);  // nms.cu
-size_t nms_workspace_bytes(int B, int N);
+               int* out_idx, int* out_count, const NmsOptions& opt, cudaStream_t st);  // nms.cu
 
 }  // namespace byolo

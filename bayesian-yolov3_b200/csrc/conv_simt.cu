@@ -224,26 +224,40 @@ __global__ void convert_kernel(const float* __restrict__ f32, T* __restrict__ ac
     }
 }
 
-int launch_pack(const float* dense, void* act, Geom g, bool act_half, cudaStream_t st) {
+// split fp16: pixel = [hi C halves | lo C halves], value = hi + lo (both conversions exact to ~2^-22 relative)
+__global__ void convert_hilo_kernel(const float* __restrict__ f32, __half* __restrict__ act, long long total, int C, int to_act) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / C;
+        const int c = (int)(i - pix * C);
+        __half* hp = act + pix * 2 * C + c;
+        if (to_act) {
+            const float v = f32[i];
+            const __half hi = __float2half_rn(v);
+            hp[0] = hi;
+            hp[C] = __float2half_rn(v - __half2float(hi));
+        } else {
+            const_cast<float*>(f32)[i] = __half2float(hp[0]) + __half2float(hp[C]);
+        }
+    }
+}
+
+static int convert(const float* dense, void* act, Geom g, int act_fmt, int to_act, cudaStream_t st) {
     const long long total = g.rows() * g.C;
     const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-    if (act_half)
-        convert_kernel<__half><<<grid, 256, 0, st>>>(dense, (__half*)act, total, 1);
+    if (act_fmt == ACT_F16_HILO)
+        convert_hilo_kernel<<<grid, 256, 0, st>>>(dense, (__half*)act, total, g.C, to_act);
+    else if (act_fmt == ACT_F16)
+        convert_kernel<__half><<<grid, 256, 0, st>>>(dense, (__half*)act, total, to_act);
     else
-        convert_kernel<float><<<grid, 256, 0, st>>>(dense, (float*)act, total, 1);
+        convert_kernel<float><<<grid, 256, 0, st>>>(dense, (float*)act, total, to_act);
     BY_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_unpack(const void* act, float* dense, Geom g, bool act_half, cudaStream_t st) {
-    const long long total = g.rows() * g.C;
-    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-    if (act_half)
-        convert_kernel<__half><<<grid, 256, 0, st>>>(dense, (__half*)const_cast<void*>(act), total, 0);
-    else
-        convert_kernel<float><<<grid, 256, 0, st>>>(dense, (float*)const_cast<void*>(act), total, 0);
-    BY_CUDA(cudaGetLastError());
-    return 0;
+int launch_pack(const float* dense, void* act, Geom g, int act_fmt, cudaStream_t st) { return convert(dense, act, g, act_fmt, 1, st); }
+
+int launch_unpack(const void* act, float* dense, Geom g, int act_fmt, cudaStream_t st) {
+    return convert(dense, const_cast<void*>(act), g, act_fmt, 0, st);
 }
 
 }  // namespace byolo

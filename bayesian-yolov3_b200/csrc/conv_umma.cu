@@ -274,9 +274,9 @@ struct DropRow {
     uint32_t t, image;
 };
 
-template <bool DROP, bool RES>
-__device__ __forceinline__ void chunk_f16(const uint32_t (&raw)[32], const float* __restrict__ bias_s, const uint4 (&res)[4],
-                                          uint4 (&o)[4], const Dropout& d, const DropRow& dr, uint32_t group_c) {
+template <bool DROP, bool RES, bool X3>
+__device__ __forceinline__ void chunk_f16(const uint32_t (&raw)[32], const float* __restrict__ bias_s, const uint4 (&res)[X3 ? 8 : 4],
+                                          uint4 (&o)[X3 ? 8 : 4], const Dropout& d, const DropRow& dr, uint32_t group_c) {
     const uint32_t thr32 = d.thr16 << 16;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -304,36 +304,32 @@ __device__ __forceinline__ void chunk_f16(const uint32_t (&raw)[32], const float
             const __half2* rh = reinterpret_cast<const __half2*>(&res[g]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(rh[j]);
+                float2 f = __half22float2(rh[j]);
+                if constexpr (X3) {                      // shortcut value = hi + lo (exact in fp32)
+                    const float2 fl = __half22float2(reinterpret_cast<const __half2*>(&res[4 + g])[j]);
+                    f.x += fl.x;
+                    f.y += fl.y;
+                }
                 v[2 * j] += f.x;
                 v[2 * j + 1] += f.y;
             }
         }
         __half2* oh = reinterpret_cast<__half2*>(&o[g]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    }
-}
-
-__device__ __forceinline__ void stage_and_store(const CUtensorMap* map_o, uint32_t stg, uint32_t stg_row, uint32_t swz, int lane,
-                                                const uint4 (&o)[4], int c, int row0) {
-    if (lane == 0) bulk_wait_read0();        // the previous store of this warp has drained the staging block
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t dst = stg_row + (((uint32_t)j ^ swz) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[j].x), "r"(o[j].y), "r"(o[j].z), "r"(o[j].w) : "memory");
-    }
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-        tma_store_2d(map_o, stg, c, row0);   // rows past the end of the tensor are clipped by the TMA unit
-        bulk_commit();
+        for (int j = 0; j < 4; ++j) {
+            oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            if constexpr (X3) {                          // lo = fp16(v - hi): the value is carried as hi + lo (22 significant bits)
+                const float2 h = __half22float2(oh[j]);
+                reinterpret_cast<__half2*>(&o[4 + g])[j] = __floats2half2_rn(v[2 * j] - h.x, v[2 * j + 1] - h.y);
+            }
+        }
     }
 }
 
 // Epilogue of the 8 epilogue warps.  KIND selects the store path and the fused extras (EpiKind in conv_umma.cuh).
-template <int CG, int EW, int KIND>
+// X3 (split-fp16 mode): activations are carried as hi + lo fp16 pairs, pixel layout [hi C | lo C]; the epilogue splits its
+// fp32 result and stores both halves (second staging block, second TMA store), the shortcut is read as hi + lo.
+template <int CG, int EW, int KIND, bool X3>
 __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const UmmaParams& p, SmemCtl* ctl, uint32_t tmem_base,
                                              uint32_t out_stage, int warp, int lane, uint32_t rank, int first_tile, int tile_step) {
     constexpr bool kF32 = KIND == EPI_F32;
@@ -341,6 +337,8 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
     constexpr bool kRes = KIND == EPI_F16_RES;
     constexpr bool kUp = KIND == EPI_UPSAMPLE;
     constexpr int CH = kF32 ? 16 : 32;
+    constexpr int NO = (X3 && !kF32) ? 8 : 4;    // uint4 per row and chunk: hi [+ lo]
+    constexpr int NP = NO / 4;                   // planes written
     const int quad = warp & 3;
     constexpr int kSplit = EW / 4;               // warps sharing a TMEM lane quadrant: they interleave the column chunks
     const int hsel = (warp - kCtlWarps) >> 2;
@@ -349,22 +347,28 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
     const uint32_t out_rows = (uint32_t)p.out_rows;
     const int nchunks = p.BN / CH;
     const int nnt_shift = p.nnt_shift, BN = p.BN, ldc = ep.ldc;
+    const int pitch = X3 && !kF32 ? 2 * ldc : ldc;           // halves per pixel of the output / shortcut buffers
     const uint32_t stg = out_stage + (uint32_t)(warp - kCtlWarps) * kStageOutBytes;
     const uint32_t stg_row = stg + lane * 64;
     const uint32_t swz = (uint32_t)((lane >> 1) & 3);
     const uint32_t acc_full0 = smem_u32(&ctl->acc_full[0]), acc_empty0 = smem_u32(&ctl->acc_empty[0]);
     const int i = quad * 32 + lane;              // row of the tile == TMEM lane
-    uint4 rnext[4] = {};
+    uint4 rnext[NO] = {};
     auto res_prefetch = [&](int t, int ch) {     // residual (shortcut) values of chunk `ch` of tile `t` for this thread's row
         if (t >= p.num_tiles || ch >= nchunks) return;
         const uint32_t r = (uint32_t)((t >> nnt_shift) * CG + (int)rank) * kTileM + (uint32_t)i;
         if (r >= out_rows) return;
-        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(ep.residual) + (size_t)r * ldc +
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(ep.residual) + (size_t)r * pitch +
                                                          (t & ((1 << nnt_shift) - 1)) * BN + ch * CH);
 #pragma unroll
         for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+        if constexpr (NO == 8) {
+            const uint4* rl = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(rp) + ldc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rnext[4 + j] = __ldg(rl + j);
+        }
     };
-    uint32_t tile_it = 0;
+    uint32_t tile_it = 0, chunk_it = 0;
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++tile_it) {
         const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
         const int m_tile = (tile >> nnt_shift) * CG + (int)rank;
@@ -392,31 +396,77 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
 #pragma unroll
             for (int k = 0; k < 4; ++k) up_q[k] = __shfl_sync(0xFFFFFFFFu, q00, (lane >> 2) + 8 * k);
         }
-        if constexpr (kRes) {
+        if constexpr (kRes && !X3) {
             if (tile_it == 0) res_prefetch(tile, hsel);      // later tiles: requested during the previous tile's last chunk
         }
-        mbar_wait(acc_full0 + 8 * as, aphase);
-        tc_fence_after();
+        // Split mode: the accumulator arrives in chunks (see the MMA issuer); every chunk is added - round to nearest - to
+        // register sums of this warp's <= 2 column chunks and its TMEM buffer is handed back at once.
+        constexpr int kSums = X3 ? 2 : 1;
+        float sums[kSums][CH];
+        if constexpr (X3) {
+            for (int c = 0; c < p.chunks_per_tile; ++c, ++chunk_it) {
+                const uint32_t cas = chunk_it & 1, cphase = (chunk_it >> 1) & 1;
+                mbar_wait(acc_full0 + 8 * cas, cphase);
+                tc_fence_after();
+                const uint32_t ctaddr = tmem_base + cas * kAccStride + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+                for (int k = 0; k < kSums; ++k) {
+                    const int ch = hsel + kSplit * k;
+                    if (ch < nchunks) {
+                        uint32_t t[32];
+                        if constexpr (kF32) tmem_ld16(ctaddr + ch * CH, t); else tmem_ld32(ctaddr + ch * CH, t);
+                        tmem_ld_wait();
+                        if (c == 0) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) sums[k][j] = __uint_as_float(t[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) sums[k][j] += __uint_as_float(t[j]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 1) mbar_arrive(acc_empty0 + 8 * cas);
+                    else mbar_arrive_cluster(acc_empty0 + 8 * cas, 0);
+                }
+            }
+        } else {
+            mbar_wait(acc_full0 + 8 * as, aphase);
+            tc_fence_after();
+        }
         const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quad * 32) << 16);
 #ifdef BYOLO_DBG_HOOKS
         if (!(p.dbg & 2))
 #endif
-        for (int ch = hsel; ch < nchunks; ch += kSplit) {
+#pragma unroll
+        for (int k = 0; k < (X3 ? kSums : 8); ++k) {
+            const int ch = hsel + kSplit * k;
+            if (ch >= nchunks) break;
             const int c0 = ch * CH;                  // column inside the tile
             uint32_t raw[32];
-            if constexpr (kF32) tmem_ld16(taddr + c0, raw); else tmem_ld32(taddr + c0, raw);
-            uint4 rcur[4] = {};
-            if constexpr (kRes) {
+            if constexpr (X3) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+                for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(sums[k][j]);
+            } else {
+                if constexpr (kF32) tmem_ld16(taddr + c0, raw); else tmem_ld32(taddr + c0, raw);
+            }
+            uint4 rcur[NO] = {};
+            if constexpr (kRes) {
+                if constexpr (X3) res_prefetch(tile, ch);        // split mode: the epilogue is off the critical path, load at use
+#pragma unroll
+                for (int j = 0; j < NO; ++j) rcur[j] = rnext[j];
                 // the shortcut values of this warp's NEXT chunk - of this tile or, after the last one, of its next tile -
                 // are requested now, a whole chunk (or an accumulator wait) ahead of their use
-                if (ch + kSplit < nchunks) res_prefetch(tile, ch + kSplit);
-                else res_prefetch(tile + tile_step, hsel);
+                if constexpr (!X3) {
+                    if (ch + kSplit < nchunks) res_prefetch(tile, ch + kSplit);
+                    else res_prefetch(tile + tile_step, hsel);
+                }
             }
-            tmem_ld_wait();
+            if constexpr (!X3) tmem_ld_wait();
             const int c = n0 + c0;
-            uint4 o4[4];                             // the 64 output bytes of this row
+            uint4 o4[NO];                            // the 64 output bytes of this row (x2: hi, lo)
             if constexpr (kF32) {
                 const float* bs = ctl->bias + c;
 #pragma unroll
@@ -426,44 +476,69 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
                                        __float_as_uint(__uint_as_float(raw[4 * j + 2]) + b.z), __float_as_uint(__uint_as_float(raw[4 * j + 3]) + b.w));
                 }
             } else {
-                chunk_f16<kDrop, kRes>(raw, ctl->bias + c, rcur, o4, ep.drop, dr, (uint32_t)c0 >> 3);
+                chunk_f16<kDrop, kRes, X3>(raw, ctl->bias + c, rcur, o4, ep.drop, dr, (uint32_t)c0 >> 3);
             }
             if constexpr (!kUp) {
-                stage_and_store(map_o, stg, stg_row, swz, lane, o4, c, m_tile * kTileM + quad * 32);
+                // the warp's 32 x 64 B block(s) -> 64B-swizzled staging -> TMA store (rows past the end are clipped by the unit)
+                // (split mode: hi then lo through the same block - its main loop is 3x longer, the epilogue has time to spare,
+                // and a second block would cost a pipeline stage)
+#pragma unroll
+                for (int pl = 0; pl < NP; ++pl) {
+                    if (lane == 0) bulk_wait_read0();    // the previous store of this warp has drained the staging block
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t dst = stg_row + (((uint32_t)j ^ swz) << 4);
+                        const uint4 v = o4[4 * pl + j];
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(map_o, stg, pl * ldc + c, m_tile * kTileM + quad * 32);
+                        bulk_commit();
+                    }
+                }
             } else {
                 // nearest-neighbour x2: every row goes to four destination pixels.  The chunk is transposed through the
                 // staging block so that one store instruction writes 8 rows x 64 contiguous bytes (full 32 B sectors).
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t dst = stg_row + (((uint32_t)j ^ swz) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o4[j].x), "r"(o4[j].y), "r"(o4[j].z), "r"(o4[j].w) : "memory");
-                }
-                __syncwarp();
                 __half* ob = reinterpret_cast<__half*>(ep.out);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t rr = (uint32_t)(lane >> 2) + 8u * k, jj = (uint32_t)lane & 3u;
-                    uint4 v;
-                    const uint32_t src = stg + rr * 64 + ((jj ^ ((rr >> 1) & 3u)) << 4);
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
-                    if (up_q[k] != 0xFFFFFFFFu) {
+                for (int pl = 0; pl < NP; ++pl) {
+                    __syncwarp();
 #pragma unroll
-                        for (int dy = 0; dy < 2; ++dy)
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t dst = stg_row + (((uint32_t)j ^ swz) << 4);
+                        const uint4 v = o4[4 * pl + j];
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    }
+                    __syncwarp();
 #pragma unroll
-                            for (int dx = 0; dx < 2; ++dx) {
-                                const size_t q = (size_t)up_q[k] + (size_t)(dy * 2 * Wo + dx);
-                                *reinterpret_cast<uint4*>(ob + q * ldc + c + jj * 8) = v;
-                            }
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t rr = (uint32_t)(lane >> 2) + 8u * k, jj = (uint32_t)lane & 3u;
+                        uint4 v;
+                        const uint32_t src = stg + rr * 64 + ((jj ^ ((rr >> 1) & 3u)) << 4);
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
+                        if (up_q[k] != 0xFFFFFFFFu) {
+#pragma unroll
+                            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                                for (int dx = 0; dx < 2; ++dx) {
+                                    const size_t q = (size_t)up_q[k] + (size_t)(dy * 2 * Wo + dx);
+                                    *reinterpret_cast<uint4*>(ob + q * pitch + pl * ldc + c + jj * 8) = v;
+                                }
+                        }
                     }
                 }
             }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-            if constexpr (CG == 1) mbar_arrive(acc_empty0 + 8 * as);
-            else mbar_arrive_cluster(acc_empty0 + 8 * as, 0);      // the leader's MMA thread waits for both CTAs
+        if constexpr (!X3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 1) mbar_arrive(acc_empty0 + 8 * as);
+                else mbar_arrive_cluster(acc_empty0 + 8 * as, 0);      // the leader's MMA thread waits for both CTAs
+            }
         }
     }
     if (!kUp && lane == 0) bulk_wait0();          // all output writes complete before the CTA retires
@@ -473,14 +548,19 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
 // 128 A rows and HALF of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) for both, every CTA runs
 // the epilogue of its own 128 accumulator rows.  Per SM and MMA cycle this moves 2/3 of the bytes of CG = 1.
 // AM: how the producer addresses the A operand (AMode in conv_umma.cuh).
-template <int CG, int AM, int EW>
+// X3: split-fp16 mode.  Every operand is a hi + lo fp16 pair (activations: pixel layout [hi C | lo C]; weights: rows
+// [0, cout_pad) hi, [cout_pad, 2 cout_pad) lo); a K block stages {A_hi, A_lo, B_hi, B_lo} and issues three MMAs per K step
+// into the same accumulator: hi*hi + hi*lo + lo*hi (lo*lo is below fp32 resolution).
+template <int CG, int AM, int EW, bool X3>
 __global__ void __launch_bounds__((kCtlWarps + EW) * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o, const UmmaParams p) {
     extern __shared__ uint8_t smem_raw[];
     // ring of {A,B} tiles, 1024B aligned (SWIZZLE_128B atoms are 1024B); output staging and control block behind it
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t kb_bytes = p.a_bytes + p.b_bytes;              // one K block of {A, B}
+    constexpr uint32_t NPL = X3 ? 2 : 1;                          // operand planes (hi [, lo])
+    const uint32_t a_span = p.a_bytes * NPL;                      // A_hi [A_lo], then B_hi [B_lo]
+    const uint32_t kb_bytes = a_span + p.b_bytes * NPL;           // one K block of {A, B}
     const uint32_t stage_bytes = kb_bytes * p.kbs;                // a stage holds kbs K blocks (8 MMAs per commit when kbs = 2)
     const uint32_t out_stage = ring + p.num_stages * stage_bytes;
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw + (ring - smem_u32(smem_raw)) + (size_t)p.num_stages * stage_bytes +
@@ -549,7 +629,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
     if (warp == 0) {
         // ================================ TMA producer, A operand (whole warp converged, one elected lane issues) =====
         const int BK = p.BK, kbt = p.kb1 + p.kb2, kb1 = p.kb1, cstride = p.stride;
-        const uint32_t a_bytes = p.a_bytes;
+        const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes;
+        const int c1_lo = p.c1_lo, c2_lo = p.c2_lo, b_lo_row = p.b_lo_row;
         const bool bsplit = p.bsplit != 0;
         uint32_t stage = 0, phase = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -588,21 +669,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                     continue;
                 }
 #endif
-                if (leader_lane && rank == 0) mbar_expect_tx(full, (bsplit ? a_bytes : kb_bytes) * nkb * CG);    // bytes of both CTAs land on the leader's barrier
+                if (leader_lane && rank == 0) mbar_expect_tx(full, (bsplit ? a_span : kb_bytes) * nkb * CG);    // bytes of both CTAs land on the leader's barrier
                 for (int j = 0; j < nkb; ++j) {
                     if (leader_lane) {
-                        if constexpr (AM == A_IM2COL) {
-                            tma_im2col_4d<CG>(sa, &map_a1, full, cb * BK, cw, chh, cn, s, r);
-                        } else if constexpr (AM == A_STACK1) {
-                            tma_im2col_5d<CG>(sa, &map_a1, full, cb * BK, cw, chh, ct, cn);
-                        } else if constexpr (AM == A_STACK2) {
-                            if (cb < kb1) tma_a2d<CG>(sa, &map_a1, full, cb * BK, m0);
-                            else tma_im2col_5d<CG>(sa, &map_a2, full, (cb - kb1) * BK, cw, chh, ct, cn);
-                        } else {
-                            if (cb < kb1) tma_a2d<CG>(sa, &map_a1, full, cb * BK, m0);
-                            else tma_a2d<CG>(sa, &map_a2, full, (cb - kb1) * BK, m0);
+#pragma unroll
+                        for (uint32_t pl = 0; pl < NPL; ++pl) {       // plane 0 = hi (or the only one), plane 1 = lo
+                            const uint32_t da = sa + pl * a_bytes;
+                            const int o1 = pl ? c1_lo : 0, o2 = pl ? c2_lo : 0;
+                            if constexpr (AM == A_IM2COL) {
+                                tma_im2col_4d<CG>(da, &map_a1, full, cb * BK + o1, cw, chh, cn, s, r);
+                            } else if constexpr (AM == A_STACK1) {
+                                tma_im2col_5d<CG>(da, &map_a1, full, cb * BK + o1, cw, chh, ct, cn);
+                            } else if constexpr (AM == A_STACK2) {
+                                if (cb < kb1) tma_a2d<CG>(da, &map_a1, full, cb * BK + o1, m0);
+                                else tma_im2col_5d<CG>(da, &map_a2, full, (cb - kb1) * BK + o2, cw, chh, ct, cn);
+                            } else {
+                                if (cb < kb1) tma_a2d<CG>(da, &map_a1, full, cb * BK + o1, m0);
+                                else tma_a2d<CG>(da, &map_a2, full, (cb - kb1) * BK + o2, m0);
+                            }
+                            if (!bsplit) tma_a2d<CG>(sa + a_span + pl * b_bytes, &map_b, full, b_k, n0b + (pl ? b_lo_row : 0));
                         }
-                        if (!bsplit) tma_a2d<CG>(sa + a_bytes, &map_b, full, b_k, n0b);
                     }
                     sa += kb_bytes;
                     b_k += BK;
@@ -620,10 +706,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         if (rank == 0) {
             const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, p.sbo_bytes, p.layout_type) >> 32);
             const uint32_t lo_fixed = 1u << 16;                      // leading-dimension field (unused for swizzled K-major)
-            const uint32_t idesc = p.idesc, a16 = p.a_bytes >> 4, kb16 = kb_bytes >> 4;
+            const uint32_t idesc = p.idesc, a16 = p.a_bytes >> 4, kb16 = kb_bytes >> 4, as16 = a_span >> 4, b16 = p.b_bytes >> 4;
             const bool bk64 = p.BK == 64;
             const uint32_t acc_full0 = smem_u32(&ctl->acc_full[0]), acc_empty0 = smem_u32(&ctl->acc_empty[0]);
             uint32_t stage = 0, phase = 0, tile_it = 0;
+          if constexpr (!X3) {
             for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++tile_it) {
                 const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
                 mbar_wait(acc_empty0 + 8 * as, aphase ^ 1);
@@ -641,7 +728,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
 #endif
                             {
                                 // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-                                const uint32_t b_lo = a_lo + a16;
+                                const uint32_t b_lo = a_lo + as16;
                                 umma_f16_lohi<CG>(d_tmem, a_lo, b_lo, desc_hi, idesc, (kb | j) != 0);
                                 umma_f16_lohi<CG>(d_tmem, a_lo + 2, b_lo + 2, desc_hi, idesc, 1);
                                 if (bk64) {
@@ -666,12 +753,63 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                 }
                 __syncwarp();
             }
+          } else {
+            // Split mode.  The tensor core adds into its fp32 accumulator with TRUNCATION (measured, tools/x3_probe.py: a
+            // signed bias of -2.8e-9 * K relative, -1.3e-5 for a 3x3x512 conv - it compounds over 75 layers), so an
+            // accumulator only ever takes one CHUNK of `chunk_stages` pipeline stages (12 MMAs); the epilogue warps drain
+            // each chunk into round-to-nearest fp32 register sums while the next chunk runs in the other accumulator.
+            const int chunk_stages = p.chunk_stages;
+            uint32_t chunk_it = 0;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+                for (int kb = 0; kb < num_kb; ++chunk_it) {
+                    const uint32_t as = chunk_it & 1, aphase = (chunk_it >> 1) & 1;
+                    mbar_wait(acc_empty0 + 8 * as, aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * kAccStride;
+                    for (int cs = 0; cs < chunk_stages && kb < num_kb; ++cs, kb += kbs) {
+                        const int nkb = min(kbs, num_kb - kb);
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t a0 = ((ring + stage * stage_bytes) >> 4) | lo_fixed;
+                            const int ksteps = bk64 ? 4 : 2;
+                            // the small cross terms first, the hi * hi terms last: every add onto a large accumulator is one
+                            // truncation at ITS ulp, whatever the size of the addend
+                            uint32_t a_hi = a0;
+                            for (int j = 0; j < nkb; ++j, a_hi += kb16) {
+                                const uint32_t b_hi = a_hi + as16, a_lo = a_hi + a16, b_lo = b_hi + b16;      // planes: A_hi A_lo B_hi B_lo
+                                for (int ks = 0; ks < ksteps; ++ks) {
+                                    const uint32_t o = 2u * ks;      // 16 elements (32 B) along K inside the swizzle atom
+                                    umma_f16_lohi<CG>(d_tmem, a_hi + o, b_lo + o, desc_hi, idesc, (cs | j | ks) != 0);   // hi * lo
+                                    umma_f16_lohi<CG>(d_tmem, a_lo + o, b_hi + o, desc_hi, idesc, 1);                     // lo * hi
+                                }
+                            }
+                            a_hi = a0;
+                            for (int j = 0; j < nkb; ++j, a_hi += kb16) {
+                                const uint32_t b_hi = a_hi + as16;
+                                for (int ks = 0; ks < ksteps; ++ks) umma_f16_lohi<CG>(d_tmem, a_hi + 2u * ks, b_hi + 2u * ks, desc_hi, idesc, 1);   // hi * hi
+                            }
+                            if constexpr (CG == 1) umma_commit(empty0 + 8 * stage);
+                            else umma_commit_2cta(empty0 + 8 * stage);
+                        }
+                        __syncwarp();
+                        if (++stage == (uint32_t)num_stages) { stage = 0; phase ^= 1; }
+                    }
+                    if (elect_one()) {          // chunk complete -> the epilogue warps drain it
+                        if constexpr (CG == 1) umma_commit(acc_full0 + 8 * as);
+                        else umma_commit_2cta(acc_full0 + 8 * as);
+                    }
+                    __syncwarp();
+                }
+            }
+          }
         }
     } else if (warp == 3 && p.bsplit) {
         // ================================ TMA producer, B operand (weights): same ring, same barriers =================
         const int BK = p.BK, BN = p.BN;
         const int n_rank = (int)rank * p.b_rows * (CG - 1);                  // CG = 2: my half of B
-        const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes;
+        const uint32_t b_bytes = p.b_bytes;
+        const int b_lo_row = p.b_lo_row;
         uint32_t stage = 0, phase = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             const int n0 = (tile & ((1 << nnt_shift) - 1)) * BN + n_rank;
@@ -681,7 +819,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
                 const uint32_t full = full0 + 8 * stage;
                 const bool leader_lane = elect_one();
-                uint32_t sb = ring + stage * stage_bytes + a_bytes;
+                uint32_t sb = ring + stage * stage_bytes + a_span;
 #ifdef BYOLO_DBG_HOOKS
                 if (p.dbg & 1) {
                     if (leader_lane && rank == 0) mbar_arrive(full);
@@ -690,9 +828,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
                     continue;
                 }
 #endif
-                if (leader_lane && rank == 0) mbar_expect_tx(full, b_bytes * nkb * CG);
+                if (leader_lane && rank == 0) mbar_expect_tx(full, b_bytes * NPL * nkb * CG);
                 for (int j = 0; j < nkb; ++j) {
-                    if (leader_lane) tma_a2d<CG>(sb, &map_b, full, b_k, n0);
+                    if (leader_lane) {
+                        tma_a2d<CG>(sb, &map_b, full, b_k, n0);
+                        if constexpr (X3) tma_a2d<CG>(sb + b_bytes, &map_b, full, b_k, n0 + b_lo_row);
+                    }
                     sb += kb_bytes;
                     b_k += BK;
                 }
@@ -710,13 +851,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
         // The residual of the next chunk is requested before the current one is processed (the first one before the
         // accumulator barrier), so its latency overlaps TMEM traffic and math.
         switch (p.epi_kind) {
-            case EPI_F16: run_epilogue<CG, EW, EPI_F16>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
-            case EPI_F16_RES: run_epilogue<CG, EW, EPI_F16_RES>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
-            case EPI_F16_DROP: run_epilogue<CG, EW, EPI_F16_DROP>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+            case EPI_F16: run_epilogue<CG, EW, EPI_F16, X3>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+            case EPI_F16_RES: run_epilogue<CG, EW, EPI_F16_RES, X3>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+            case EPI_F16_DROP: run_epilogue<CG, EW, EPI_F16_DROP, X3>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
             default:
                 if constexpr (CG == 1 && AM == A_TILED) {
-                    if (p.epi_kind == EPI_F32) run_epilogue<CG, EW, EPI_F32>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
-                    else run_epilogue<CG, EW, EPI_UPSAMPLE>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
+                    if (p.epi_kind == EPI_F32) run_epilogue<CG, EW, EPI_F32, X3>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
+                    else run_epilogue<CG, EW, EPI_UPSAMPLE, X3>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
                 }
                 break;
         }
@@ -817,6 +958,37 @@ static FastDiv make_fastdiv(uint32_t d) {
     return f;
 }
 
+// Experiment switches (BYOLO_BN / BYOLO_CG / BYOLO_DBG / BYOLO_BSPLIT / BYOLO_KBS, profiles/r01/exp_v8_switches.txt) exist only
+// in builds with -DBYOLO_DBG_HOOKS; the product library never reads the environment.
+static int dbg_env(const char* name, int dflt = 0) {
+#ifdef BYOLO_DBG_HOOKS
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
+}
+
+static const void* kernel_variant(int cg, int amode, int x3) {
+#define BYOLO_KV(CG_, AM_) (x3 ? (const void*)conv_umma_kernel<CG_, AM_, 8, true> : (const void*)conv_umma_kernel<CG_, AM_, 8, false>)
+    if (cg == 2) {
+        switch (amode) {
+            case A_IM2COL: return BYOLO_KV(2, A_IM2COL);
+            case A_STACK1: return BYOLO_KV(2, A_STACK1);
+            case A_STACK2: return BYOLO_KV(2, A_STACK2);
+            default: return BYOLO_KV(2, A_TILED);
+        }
+    }
+    switch (amode) {
+        case A_IM2COL: return BYOLO_KV(1, A_IM2COL);
+        case A_STACK1: return BYOLO_KV(1, A_STACK1);
+        case A_STACK2: return BYOLO_KV(1, A_STACK2);
+        default: return BYOLO_KV(1, A_TILED);
+    }
+#undef BYOLO_KV
+}
+
 int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     std::memset(L, 0, sizeof(*L));
     UmmaParams& p = L->p;
@@ -837,6 +1009,12 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.kb1 = C1 / p.BK;
     p.kb2 = C2 / p.BK;
     p.BN = std::min(q.cout_pad, 256);
+    const bool x3 = q.x3 != 0;
+    p.x3 = x3 ? 1 : 0;
+    const int npl = x3 ? 2 : 1;                                   // operand planes: hi [, lo]
+    // split mode: N tiles of <= 128 columns - each epilogue thread keeps round-to-nearest register sums of its <= 64 columns
+    // (chunked accumulation, see the MMA issuer) and {A_hi, A_lo, B_hi, B_lo} stages stay <= 64 KB
+    if (x3) p.BN = std::min(p.BN, 128);
     {
         // Wave quantisation: a layer runs ceil(tiles / resident tiles) rounds of tiles.  Small-M layers (19x19, 38x38 maps
         // of a 16-image batch) fill 1.24 / 2.46 rounds with 256-wide tiles; 128-wide tiles cost the same MMA rate
@@ -847,8 +1025,8 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
         const bool pair = q.k == 3;                                                          // CTA pairs (decided below)
         const long long m_units = (m_rows + (pair ? 255 : 127)) / (pair ? 256 : 128);
         const int slots = pair ? sms_ / 2 : sms_;
-        static const int bn_env = getenv("BYOLO_BN") ? atoi(getenv("BYOLO_BN")) : 0;      // 256: never narrow the tile
-        if (q.cout_pad >= 256 && q.cout_pad % 256 == 0 && bn_env != 256) {
+        const int bn_env = dbg_env("BYOLO_BN");                                            // 256: never narrow the tile
+        if (p.BN == 256 && q.cout_pad % 256 == 0 && bn_env != 256) {
             const long long r256 = (m_units * (q.cout_pad / 256) + slots - 1) / slots * 2;      // cost in 128-column units
             const long long r128 = (m_units * (q.cout_pad / 128) + slots - 1) / slots;
             if (r128 * 10 <= r256 * 9) p.BN = 128;       // only when a tenth of the rounds goes away (narrow tiles reload A twice as often)
@@ -861,16 +1039,16 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.amode = q.k == 3 ? A_IM2COL : (t1 > 1 ? A_STACK1 : (t2 > 1 ? A_STACK2 : A_TILED));
     p.stride = q.stride;
     // CTA pairs for the feed-bound shapes: 3x3 stride-1 convs with wide N tiles
-    static const int cg_env = getenv("BYOLO_CG") ? atoi(getenv("BYOLO_CG")) : 0;     // 1 = force off, 2 = default policy
+    const int cg_env = dbg_env("BYOLO_CG");                                          // 1 = force off, 2 = default policy
     // (measured per layer, profiles/r01/exp_v8_switches.txt: pairs win on every 3x3 conv, 5-23% fewer cycles)
     p.cg = (cg_env != 1 && q.k == 3 && p.BN >= 64) ? 2 : 1;
     // wide (N tile 256) 1x1 convs: pairs halve the weight traffic per SM: -10..-12% cycles on the 512/768 -> 256 and
     // 1024 -> 512 layers (exp_v8_switches.txt)
     if (cg_env != 1 && q.k == 1 && p.BN >= 256 && p.BK == 64 && q.ep.out_mode == OUT_DENSE) p.cg = 2;
     if (cg_env == 5 && q.k == 1 && p.BN >= 128 && p.BK == 64 && q.ep.out_mode == OUT_DENSE) p.cg = 2;      // experiment: N tile 128 too
+    if (x3 && q.k == 1 && p.BN >= 128 && p.BK == 64 && q.ep.out_mode == OUT_DENSE) p.cg = 2;                // split mode: N tile is capped at 128
     p.b_rows = p.BN / p.cg;
-    static const int dbg_env = getenv("BYOLO_DBG") ? atoi(getenv("BYOLO_DBG")) : 0;
-    p.dbg = dbg_env;
+    p.dbg = dbg_env("BYOLO_DBG");
     p.gout.S = g.S;
     p.gout.H = g.H / q.stride;
     p.gout.W = g.W / q.stride;
@@ -904,45 +1082,52 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.b_bytes = p.b_rows * swz;
     // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 for a CTA pair)
     p.idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((kTileM * p.cg) >> 4) << 24);
-    static const int bsplit_env = getenv("BYOLO_BSPLIT") ? atoi(getenv("BYOLO_BSPLIT")) : 1;
+    const int bsplit_env = dbg_env("BYOLO_BSPLIT", 1);
     // 8 epilogue warps.  12 and 16 were measured: no gain / slower (16 caps the block at 96 registers per thread and the
     // extra staging blocks cost a pipeline stage), profiles/r01/exp_v8_switches.txt.
     p.epi_warps = 8;
     p.bsplit = bsplit_env;
     const int budget = 227 * 1024 - 1024 - (int)sizeof(SmemCtl) - p.epi_warps * kStageOutBytes - 64;
-    static const int kbs_env = getenv("BYOLO_KBS") ? atoi(getenv("BYOLO_KBS")) : 0;
+    const int kbs_env = dbg_env("BYOLO_KBS");
+    const int kb_bytes = npl * (p.a_bytes + p.b_bytes);           // one K block: {A, B} or {A_hi, A_lo, B_hi, B_lo}
     const int num_kb = p.taps * (p.kb1 + p.kb2);
     // K blocks per stage: every stage costs one barrier round trip and one tcgen05.commit (~400 cycles of issue
     // overhead measured on the short layers), so a stage should carry >= 8 MMAs: 2 blocks of 64 channels or 4 of 32 -
     // as long as >= 3 stages still fit.
     p.kbs = 1;
     if (kbs_env >= 2) {                                   // experiment: force it wherever two stages still fit
-        if (num_kb >= kbs_env && budget / (kbs_env * (p.a_bytes + p.b_bytes)) >= 2) p.kbs = kbs_env;
-        else if (num_kb >= 2 && budget / (2 * (p.a_bytes + p.b_bytes)) >= 3) p.kbs = 2;
+        if (num_kb >= kbs_env && budget / (kbs_env * kb_bytes) >= 2) p.kbs = kbs_env;
+        else if (num_kb >= 2 && budget / (2 * kb_bytes) >= 3) p.kbs = 2;
     } else if (kbs_env != 1) {
-        for (int cand = (p.BK == 64 ? 2 : 4); cand >= 2; cand /= 2)
-            if (num_kb >= cand && budget / (cand * (p.a_bytes + p.b_bytes)) >= 3) { p.kbs = cand; break; }
+        // split mode issues 3 MMAs per K step: one 64-channel block (or two 32-channel blocks) already carries 12
+        for (int cand = (p.BK == 64 ? 2 : 4) / npl; cand >= 2; cand /= 2)
+            if (num_kb >= cand && budget / (cand * kb_bytes) >= 3) { p.kbs = cand; break; }
     }
-    const int stage_bytes = p.kbs * (p.a_bytes + p.b_bytes);
-    p.num_stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
+    const int stage_bytes = p.kbs * kb_bytes;
+    BY_REQUIRE(budget / stage_bytes >= 2, "conv tile does not fit two pipeline stages in shared memory");
+    p.chunk_stages = 1;                                           // split mode: 12 MMAs (8 cross terms, then 4 hi * hi) per accumulator chunk
+    p.chunks_per_tile = ((num_kb + p.kbs - 1) / p.kbs + p.chunk_stages - 1) / p.chunk_stages;
+    p.num_stages = std::min(kMaxStages, budget / stage_bytes);
     L->smem_bytes = p.num_stages * stage_bytes + 1024 + sizeof(SmemCtl) + p.epi_warps * kStageOutBytes + 64;
 
     const uint32_t one[5] = {1, 1, 1, 1, 1};
     p.num_m_tiles = (int)((p.out_rows + kTileM - 1) / kTileM);
     const uint32_t box_a[2] = {(uint32_t)p.BK, (uint32_t)kTileM};
     if (p.amode == A_IM2COL) {
-        const uint64_t d[4] = {(uint64_t)C1, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.S};
-        const uint64_t st[3] = {(uint64_t)C1 * 2, (uint64_t)C1 * 2 * g.W, (uint64_t)C1 * 2 * g.W * g.H};
+        const uint64_t P1 = (uint64_t)C1 * npl;                    // halves per pixel: [hi C1 | lo C1] in split mode
+        const uint64_t d[4] = {P1, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.S};
+        const uint64_t st[3] = {P1 * 2, P1 * 2 * g.W, P1 * 2 * g.W * g.H};
         if (int e = make_im2col_map(&L->a1, q.in1, 4, d, st, -1, q.stride, p.BK, kTileM, swz)) return e;
         L->a2 = L->a1;
     } else {
         auto stacked = [&](CUtensorMap* m, const void* base, int C, int T) {
-            const uint64_t d[5] = {(uint64_t)C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)T, (uint64_t)(g.S / T)};
-            const uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)C * 2 * g.W, 0ull, (uint64_t)C * 2 * g.W * g.H};
+            const uint64_t P = (uint64_t)C * npl;
+            const uint64_t d[5] = {P, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)T, (uint64_t)(g.S / T)};
+            const uint64_t st[4] = {P * 2, P * 2 * g.W, 0ull, P * 2 * g.W * g.H};
             return make_im2col_map(m, base, 5, d, st, 0, 1, p.BK, kTileM, swz);
         };
         auto tiled = [&](CUtensorMap* m, const void* base, int C) {
-            const uint64_t d[2] = {(uint64_t)C, (uint64_t)g.rows()}, st[1] = {(uint64_t)C * 2};
+            const uint64_t d[2] = {(uint64_t)C * npl, (uint64_t)g.rows()}, st[1] = {(uint64_t)C * npl * 2};
             return make_map(m, base, 2, d, st, box_a, one, swz);
         };
         if (p.amode == A_STACK1) { if (int e = stacked(&L->a1, q.in1, C1, t1)) return e; }
@@ -953,7 +1138,7 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     }
     {
         const uint64_t K = (uint64_t)p.taps * (C1 + C2);
-        uint64_t d[2] = {K, (uint64_t)q.cout_pad}, s[1] = {K * 2};
+        uint64_t d[2] = {K, (uint64_t)q.cout_pad * npl}, s[1] = {K * 2};      // split mode: lo rows follow the cout_pad hi rows
         uint32_t box[2] = {(uint32_t)p.BK, (uint32_t)p.b_rows};
         if (int e = make_map(&L->b, q.w16, 2, d, s, box, one, swz)) return e;
     }
@@ -961,10 +1146,14 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     if (p.epi_kind != EPI_UPSAMPLE) {
         // output map: [rows, ldc] of the dense output, 32 x 64 B boxes
         const bool f32 = p.epi_kind == EPI_F32;
-        uint64_t d[2] = {(uint64_t)q.ep.ldc, (uint64_t)p.out_rows}, st[1] = {(uint64_t)q.ep.ldc * (f32 ? 4 : 2)};
+        const uint64_t pitch = (uint64_t)q.ep.ldc * (f32 ? 1 : npl);
+        uint64_t d[2] = {pitch, (uint64_t)p.out_rows}, st[1] = {pitch * (f32 ? 4 : 2)};
         uint32_t box[2] = {(uint32_t)(f32 ? 16 : 32), 32u};
         if (int e = make_map(&L->o, q.ep.out, 2, d, st, box, one, 64, f32)) return e;
     }
+    p.c1_lo = C1;
+    p.c2_lo = C2;
+    p.b_lo_row = q.cout_pad;
     p.num_tiles = ((p.num_m_tiles + p.cg - 1) / p.cg) * p.num_n_tiles;      // CG = 2: tiles are pairs of M tiles
     int dev = 0, sms = 0;
     BY_CUDA(cudaGetDevice(&dev));
@@ -977,17 +1166,8 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     {
         std::lock_guard<std::mutex> lock(attr_mutex);
         if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-            auto set = [&](const void* f) {
-                if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            };
-            set((const void*)conv_umma_kernel<2, A_IM2COL, 8>);
-            set((const void*)conv_umma_kernel<2, A_TILED, 8>);
-            set((const void*)conv_umma_kernel<2, A_STACK1, 8>);
-            set((const void*)conv_umma_kernel<2, A_STACK2, 8>);
-            set((const void*)conv_umma_kernel<1, A_TILED, 8>);
-            set((const void*)conv_umma_kernel<1, A_IM2COL, 8>);
-            set((const void*)conv_umma_kernel<1, A_STACK1, 8>);
-            set((const void*)conv_umma_kernel<1, A_STACK2, 8>);
+            for (int v = 0; v < 16 && attr_err == cudaSuccess; ++v)
+                attr_err = cudaFuncSetAttribute(kernel_variant(v & 1 ? 2 : 1, (v >> 1) & 3, v >> 3), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (attr_err == cudaSuccess && dev >= 0 && dev < 64) attr_done[dev] = true;
         }
     }
@@ -1012,19 +1192,9 @@ int umma_launch(const UmmaLaunch& L, cudaStream_t st) {
         attr[1].val.clusterDim.y = 1;
         attr[1].val.clusterDim.z = 1;
         cfg.numAttrs = 2;
-        if (L.p.amode == A_IM2COL) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_IM2COL, 8>, L.a1, L.a2, L.b, L.o, L.p));
-        else if (L.p.amode == A_STACK1) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_STACK1, 8>, L.a1, L.a2, L.b, L.o, L.p));
-        else if (L.p.amode == A_STACK2) BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_STACK2, 8>, L.a1, L.a2, L.b, L.o, L.p));
-        else BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<2, A_TILED, 8>, L.a1, L.a2, L.b, L.o, L.p));
-    } else if (L.p.amode == A_IM2COL) {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_IM2COL, 8>, L.a1, L.a2, L.b, L.o, L.p));
-    } else if (L.p.amode == A_STACK1) {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK1, 8>, L.a1, L.a2, L.b, L.o, L.p));
-    } else if (L.p.amode == A_STACK2) {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_STACK2, 8>, L.a1, L.a2, L.b, L.o, L.p));
-    } else {
-        BY_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, A_TILED, 8>, L.a1, L.a2, L.b, L.o, L.p));
     }
+    void* args[5] = {(void*)&L.a1, (void*)&L.a2, (void*)&L.b, (void*)&L.o, (void*)&L.p};
+    BY_CUDA(cudaLaunchKernelExC(&cfg, kernel_variant(L.p.cg, L.p.amode, L.p.x3), args));
     return 0;
 }
 

@@ -47,6 +47,11 @@ struct UmmaParams {
     int epi_kind;                  // EpiKind
     int nnt_shift;                 // log2(num_n_tiles)
     FastDiv fd_plane, fd_w, fd_h, fd_T;   // output row -> (sample, y, x); sample -> (image, MC sample t)
+    int x3;                        // split-fp16 mode: operands are hi + lo fp16 pairs, 3 MMAs per K step
+    int c1_lo, c2_lo;              // channel coordinate of the lo plane in the in1 / in2 tensor maps (= C1 / C2)
+    int b_lo_row;                  // row of the first lo weight row in the B tensor map (= cout_pad)
+    int chunk_stages;              // split mode: pipeline stages per accumulator chunk (the epilogue sums the chunks in fp32, RN)
+    int chunks_per_tile;
     int dbg;                       // experiments only (-DBYOLO_DBG_HOOKS, BYOLO_DBG): 1 = no operand TMA loads, 2 = no epilogue work, 4 = no MMAs
     unsigned long long* clk;       // profiling: {clock64, globaltimer} at start and end of CTA 0 (effective SM clock), or null
 };

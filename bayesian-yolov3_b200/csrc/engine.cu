@@ -62,7 +62,10 @@ struct LayerWeights {
 };
 
 // Folds BN into (weights, shift) and uploads both layouts.  kernel: HWIO fp32; bn = beta,gamma,mean,var | nullptr.
-static int fold_and_upload(const LayerDef& d, const float* kernel, const float* bn, const float* bias, LayerWeights* out) {
+// split: the fp16 matrix carries 2*cout_pad rows - fp16(v) in rows [0, cout_pad), fp16(v - hi) in the rows behind them
+// (split-fp16 mode, BYOLO_PREC_FP16X3).
+static int fold_and_upload(const LayerDef& d, const float* kernel, const float* bn, const float* bias, LayerWeights* out,
+                           bool split = false) {
     const int K = d.k * d.k * d.cin;
     const int cp = (d.cout + 15) / 16 * 16;
     std::vector<float> scale(d.cout, 1.f), shift(cp, 0.f);
@@ -76,22 +79,29 @@ static int fold_and_upload(const LayerDef& d, const float* kernel, const float* 
         }
     }
     std::vector<float> w32((size_t)K * cp, 0.f);
-    std::vector<__half> w16((size_t)cp * K, __float2half(0.f));
+    std::vector<__half> w16((size_t)cp * K * (split ? 2 : 1), __float2half(0.f));
     for (int kk = 0; kk < K; ++kk)
         for (int c = 0; c < d.cout; ++c) {
             const float v = kernel[(size_t)kk * d.cout + c] * scale[c];   // HWIO flattened == [K][cout]
             w32[(size_t)kk * cp + c] = v;
-            w16[(size_t)c * K + kk] = __float2half_rn(v);
+            const __half hi = __float2half_rn(v);
+            w16[(size_t)c * K + kk] = hi;
+            if (split) w16[((size_t)cp + c) * K + kk] = __float2half_rn(v - __half2float(hi));
         }
     out->K = K;
     out->cout_pad = cp;
-    BY_CUDA(cudaMalloc(&out->bias, sizeof(float) * cp));
-    BY_CUDA(cudaMalloc(&out->w32, sizeof(float) * w32.size()));
-    BY_CUDA(cudaMalloc(&out->w16, sizeof(__half) * w16.size()));
-    BY_CUDA(cudaMemcpy(out->bias, shift.data(), sizeof(float) * cp, cudaMemcpyHostToDevice));
-    BY_CUDA(cudaMemcpy(out->w32, w32.data(), sizeof(float) * w32.size(), cudaMemcpyHostToDevice));
-    BY_CUDA(cudaMemcpy(out->w16, w16.data(), sizeof(__half) * w16.size(), cudaMemcpyHostToDevice));
-    return 0;
+    auto upload = [&]() -> int {
+        BY_CUDA(cudaMalloc(&out->bias, sizeof(float) * cp));
+        BY_CUDA(cudaMalloc(&out->w32, sizeof(float) * w32.size()));
+        BY_CUDA(cudaMalloc(&out->w16, sizeof(__half) * w16.size()));
+        BY_CUDA(cudaMemcpy(out->bias, shift.data(), sizeof(float) * cp, cudaMemcpyHostToDevice));
+        BY_CUDA(cudaMemcpy(out->w32, w32.data(), sizeof(float) * w32.size(), cudaMemcpyHostToDevice));
+        BY_CUDA(cudaMemcpy(out->w16, w16.data(), sizeof(__half) * w16.size(), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    const int rc = upload();
+    if (rc) out->release();          // no partial allocations survive a failure
+    return rc;
 }
 
 struct Buffer {
@@ -163,8 +173,10 @@ struct byolo_engine {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     int N = 0, D = 0, obj_idx = 0, cls_start = 0;
     int gh[3], gw[3];
-    bool act_half() const { return cfg.precision != BYOLO_PREC_FP32; }
-    size_t esize() const { return act_half() ? 2 : 4; }
+    bool umma() const { return cfg.precision == BYOLO_PREC_FP16 || cfg.precision == BYOLO_PREC_FP16X3; }
+    bool x3() const { return cfg.precision == BYOLO_PREC_FP16X3; }
+    int act_fmt() const { return cfg.precision == BYOLO_PREC_FP32 ? ACT_F32 : (x3() ? ACT_F16_HILO : ACT_F16); }
+    size_t esize() const { return act_fmt() == ACT_F16 ? 2 : 4; }      // bytes per activation element (hi + lo pair: 4)
     bool mc() const { return cfg.variant == BYOLO_EPISTEMIC; }
     int samples(int B) const { return mc() ? B * cfg.T : B; }
     ~byolo_engine() {
@@ -232,6 +244,7 @@ static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int res
     p.cout_pad = w.cout_pad;
     p.w16 = w.w16;
     p.w32 = w.w32;
+    p.x3 = e->x3();
     p.ep.bias = w.bias;
     p.ep.residual = residual >= 0 ? pl->bufs[residual].ptr : nullptr;
     p.ep.out = pl->bufs[ob].ptr;
@@ -244,7 +257,7 @@ static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int res
     p.ep.drop.T = e->cfg.T;
     p.ep.drop.thr16 = (uint32_t)std::lround((double)e->cfg.drop_prob * 65536.0);
     p.ep.drop.keep_scale = 1.0f / (1.0f - e->cfg.drop_prob);
-    if (e->cfg.precision == BYOLO_PREC_FP16)
+    if (e->umma())
         if (int r = umma_prepare(p, &st.ul)) return r;
     pl->steps.push_back(st);
     pl->conv_out[li] = ob;
@@ -352,13 +365,13 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
         if (prof) BY_CUDA(cudaEventRecord(pl->ev[ei++], st));
         if (s.kind == STEP_STEM) {
             const LayerWeights& w = e->weights[0];
-            if (c.precision == BYOLO_PREC_FP16) {
-                if (int r = launch_stem_mma(img, pl->B, c.height, c.width, w.w16, w.bias, pl->bufs[s.out_buf].ptr, st)) return r;
-            } else if (int r = launch_stem(img, pl->B, c.height, c.width, w.w32, w.bias, pl->bufs[s.out_buf].ptr, e->act_half(), st)) {
+            if (e->umma()) {
+                if (int r = launch_stem_mma(img, pl->B, c.height, c.width, w.w16, w.bias, pl->bufs[s.out_buf].ptr, e->x3(), st)) return r;
+            } else if (int r = launch_stem(img, pl->B, c.height, c.width, w.w32, w.bias, pl->bufs[s.out_buf].ptr, e->act_fmt() == ACT_F16, st)) {
                 return r;
             }
         } else {
-            if (c.precision == BYOLO_PREC_FP16) {
+            if (e->umma()) {
                 Dropout& d = s.ul.p.ep.drop;
                 d.seed_lo = (uint32_t)seed; d.seed_hi = (uint32_t)(seed >> 32); d.image0 = image0;
                 s.ul.p.clk = prof ? pl->clk + 4 * (ei - 1) : nullptr;
@@ -366,7 +379,7 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
             } else {
                 Dropout& d = s.prob.ep.drop;
                 d.seed_lo = (uint32_t)seed; d.seed_hi = (uint32_t)(seed >> 32); d.image0 = image0;
-                if (int r = launch_conv_simt(s.prob, e->act_half(), st)) return r;
+                if (int r = launch_conv_simt(s.prob, e->act_fmt() == ACT_F16, st)) return r;
             }
         }
     }
@@ -399,7 +412,7 @@ static int run_forward(byolo_engine* e, Plan* pl, const float* img, uint64_t see
 // =====================================================================================================================
 extern "C" {
 
-int byolo_version(void) { return 1; }
+int byolo_version(void) { return 2; }
 const char* byolo_last_error(void) { return g_err.c_str(); }
 
 int byolo_create(const byolo_config* cfg, byolo_handle* out) {
@@ -409,7 +422,7 @@ int byolo_create(const byolo_config* cfg, byolo_handle* out) {
                "image size must be a multiple of 32 (yolov3.py:207-211)");
     BY_REQUIRE(cfg->cls_cnt >= 1 && cfg->cls_cnt <= 16, "cls_cnt must be in [1,16]");
     BY_REQUIRE(cfg->max_batch >= 1, "max_batch must be >= 1");
-    BY_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, "unknown precision");
+    BY_REQUIRE(cfg->precision >= 0 && cfg->precision <= 3, "unknown precision");
     BY_REQUIRE(cfg->variant != BYOLO_EPISTEMIC || cfg->T >= 1, "epistemic model needs T >= 1 (yolov3.py:467-468)");
     BY_REQUIRE(cfg->drop_prob >= 0.f && cfg->drop_prob < 1.f, "drop_prob must be in [0,1)");
     int ndev = 0;
@@ -448,11 +461,8 @@ int byolo_load_weights(byolo_handle h, const void* blob, size_t bytes) {
     BY_REQUIRE(n == (int)h->layers.size(), "weight blob has the wrong number of layers");
     BY_REQUIRE(bytes >= 8 + (size_t)24 * n, "weight blob truncated");
     const int32_t* tab = hdr + 2;
+    // validate the whole blob before touching the engine: a bad blob leaves the previous weights in place
     size_t off = 8 + (size_t)24 * n;
-    for (auto& w : h->weights) w.release();
-    h->weights.assign(n, LayerWeights());
-    h->plans.clear();
-    h->last_plan = nullptr;
     for (int i = 0; i < n; ++i) {
         const LayerDef& d = h->layers[i];
         BY_REQUIRE(tab[6 * i] == d.k && tab[6 * i + 1] == d.s && tab[6 * i + 2] == d.cin && tab[6 * i + 3] == d.cout &&
@@ -460,13 +470,32 @@ int byolo_load_weights(byolo_handle h, const void* blob, size_t bytes) {
                    "weight blob layer table does not match the model variant");
         const size_t nv = (size_t)(d.bn ? 4 : 1) * d.cout, nk = (size_t)d.k * d.k * d.cin * d.cout;
         BY_REQUIRE(off + 4 * (nv + nk) <= bytes, "weight blob truncated");
-        const float* vec = (const float*)((const char*)blob + off);
-        const float* kern = vec + nv;
-        if (int r = fold_and_upload(d, kern, d.bn ? vec : nullptr, d.bn ? nullptr : vec, &h->weights[i])) return r;
         off += 4 * (nv + nk);
     }
     BY_REQUIRE(off == bytes, "weight blob has trailing bytes");     // darknet.py:66 `assert ptr == len(weights)`
-    BY_CUDA(cudaDeviceSynchronize());
+    // upload into a fresh table and swap on success; on a CUDA failure the partial table is released and the engine is
+    // left without weights (loaded = false) rather than with dangling pointers
+    h->loaded = false;
+    h->plans.clear();
+    h->last_plan = nullptr;
+    for (auto& w : h->weights) w.release();
+    h->weights.clear();
+    std::vector<LayerWeights> fresh(n);
+    off = 8 + (size_t)24 * n;
+    int rc = 0;
+    for (int i = 0; i < n && !rc; ++i) {
+        const LayerDef& d = h->layers[i];
+        const size_t nv = (size_t)(d.bn ? 4 : 1) * d.cout, nk = (size_t)d.k * d.k * d.cin * d.cout;
+        const float* vec = (const float*)((const char*)blob + off);
+        rc = fold_and_upload(d, vec + nv, d.bn ? vec : nullptr, d.bn ? nullptr : vec, &fresh[i], h->x3());
+        off += 4 * (nv + nk);
+    }
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("byolo_load_weights: device synchronisation failed"); rc = -2; }
+    if (rc) {
+        for (auto& w : fresh) w.release();
+        return rc;
+    }
+    h->weights.swap(fresh);
     h->loaded = true;
     return 0;
 }
@@ -491,19 +520,32 @@ int byolo_forward(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed
 int byolo_nms(const float* rows_dev, int32_t B, int32_t N, int32_t D, int32_t obj_idx, float iou_thr, int32_t max_out,
               float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev, void* stream) {
     BY_REQUIRE(rows_dev && out_rows_dev && out_count_dev, "null argument");
-    return launch_nms(rows_dev, B, N, D, obj_idx, iou_thr, max_out, out_rows_dev, out_idx_dev, out_count_dev, nullptr, 0,
+    return launch_nms(rows_dev, B, N, D, obj_idx, iou_thr, max_out, out_rows_dev, out_idx_dev, out_count_dev, NmsOptions{},
                       (cudaStream_t)stream);
 }
 
-int byolo_detect(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
-                 int32_t max_out, float* rows_dev, float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev,
-                 void* stream) {
-    BY_REQUIRE(h && img_dev && out_rows_dev && out_count_dev, "null argument");
+int byolo_nms_ex(const float* rows_dev, int32_t B, int32_t N, int32_t D, int32_t obj_idx, float iou_thr, int32_t max_out,
+                 float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev, int32_t packed, int32_t force_cluster_size,
+                 int32_t force_chunked, void* stream) {
+    BY_REQUIRE(rows_dev && out_rows_dev, "null argument");
+    BY_REQUIRE(packed || out_count_dev, "pass out_count_dev or ask for the packed layout");
+    NmsOptions opt;
+    opt.packed = packed != 0;
+    opt.force_cs = force_cluster_size;
+    opt.force_chunked = force_chunked != 0;
+    return launch_nms(rows_dev, B, N, D, obj_idx, iou_thr, max_out, out_rows_dev, out_idx_dev, out_count_dev, opt, (cudaStream_t)stream);
+}
+
+static int detect_impl(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
+                       int32_t max_out, float* rows_dev, float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev,
+                       bool packed, void* stream) {
     Plan* pl;
     if (int r = get_plan(h, B, &pl)) return r;
     float* rows = rows_dev ? rows_dev : pl->rows_scratch;
     if (int r = run_forward(h, pl, img_dev, seed, image_index0, rows, (cudaStream_t)stream)) return r;
-    if (int r = launch_nms(rows, B, h->N, h->D, h->obj_idx, iou_thr, max_out, out_rows_dev, out_idx_dev, out_count_dev, nullptr, 0,
+    NmsOptions opt;
+    opt.packed = packed;
+    if (int r = launch_nms(rows, B, h->N, h->D, h->obj_idx, iou_thr, max_out, out_rows_dev, out_idx_dev, out_count_dev, opt,
                            (cudaStream_t)stream))
         return r;
     if (h->profiling) { BY_CUDA(cudaEventRecord(pl->ev.back(), (cudaStream_t)stream)); pl->ev_recorded = true; }
@@ -512,6 +554,19 @@ int byolo_detect(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed,
         ++pl->coarse_n;
     }
     return 0;
+}
+
+int byolo_detect(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
+                 int32_t max_out, float* rows_dev, float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev,
+                 void* stream) {
+    BY_REQUIRE(h && img_dev && out_rows_dev && out_count_dev, "null argument");
+    return detect_impl(h, img_dev, B, seed, image_index0, iou_thr, max_out, rows_dev, out_rows_dev, out_idx_dev, out_count_dev, false, stream);
+}
+
+int byolo_detect_packed(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
+                        int32_t max_out, float* out_packed_dev, int32_t* out_idx_dev, void* stream) {
+    BY_REQUIRE(h && img_dev && out_packed_dev, "null argument");
+    return detect_impl(h, img_dev, B, seed, image_index0, iou_thr, max_out, nullptr, out_packed_dev, out_idx_dev, nullptr, true, stream);
 }
 
 int byolo_profile(byolo_handle h, int32_t enable) {
@@ -672,19 +727,26 @@ int byolo_decode(byolo_handle h, const float* raw0_dev, const float* raw1_dev, c
 int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_dev, int32_t S, int32_t H, int32_t W,
                      int32_t cin1, int32_t cin2, int32_t k, int32_t stride, int32_t cout, const float* kernel_host,
                      const float* bn_host, const float* bias_host, const float* residual_dev, int32_t upsample,
-                     int32_t dropout_layer, int32_t T, uint64_t seed, int32_t image_index0, float drop_prob, float* out_dev,
-                     void* stream) {
+                     int32_t dropout_layer, int32_t T, uint64_t seed, int32_t image_index0, float drop_prob, int32_t t1, int32_t t2,
+                     float* out_dev, void* stream) {
     BY_REQUIRE(in1_dev && kernel_host && out_dev, "null argument");
-    BY_REQUIRE(precision >= 0 && precision <= 2, "unknown precision");
+    t1 = t1 > 1 ? t1 : 1;
+    t2 = t2 > 1 ? t2 : 1;
+    BY_REQUIRE(S % t1 == 0 && S % t2 == 0, "S must be a multiple of the stacking factors");
+    BY_REQUIRE((t1 == 1 && t2 == 1) || k == 1, "MC-stacked sources only feed 1x1 convs");
+    BY_REQUIRE(!(t1 > 1 && in2_dev) && !(t2 > 1 && !in2_dev), "stacked source: in1 alone, or in2 of a concat");
+    BY_REQUIRE(precision >= 0 && precision <= 3, "unknown precision");
     BY_REQUIRE((bn_host != nullptr) != (bias_host != nullptr), "pass exactly one of bn / bias");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool half = precision != BYOLO_PREC_FP32;
-    const size_t es = half ? 2 : 4;
+    const bool x3 = precision == BYOLO_PREC_FP16X3, umma = x3 || precision == BYOLO_PREC_FP16;
+    const int half = precision == BYOLO_PREC_FP32 ? ACT_F32 : (x3 ? ACT_F16_HILO : ACT_F16);      // activation format
+    const size_t es = half == ACT_F16 ? 2 : 4;
     LayerDef d{k, stride, cin1 + cin2, cout, bn_host != nullptr, dropout_layer >= 0};
     LayerWeights w;
-    int rc = fold_and_upload(d, kernel_host, bn_host, bias_host, &w);
+    int rc = fold_and_upload(d, kernel_host, bn_host, bias_host, &w, x3);
     void *p1 = nullptr, *p2 = nullptr, *pr = nullptr, *po = nullptr;
-    const Geom g1{S, H, W, cin1}, g2{S, H, W, cin2};
+    const Geom g1{S / t1, H, W, cin1}, g2{S / t2, H, W, cin2};      // what the caller's buffers hold
+    const Geom gc{S, H, W, cin1};                                   // what the conv sees
     const int Ho = H / stride, Wo = W / stride;
     const bool dense = bn_host == nullptr;
     const Geom go{S, upsample ? 2 * Ho : Ho, upsample ? 2 * Wo : Wo, dense ? w.cout_pad : cout};
@@ -712,12 +774,13 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
     if (!rc && in2_dev) rc = launch_pack(in2_dev, p2, g2, half, st);
     if (!rc && residual_dev) rc = launch_pack(residual_dev, pr, go, half, st);
     if (!rc && stem) {
-        rc = (precision == BYOLO_PREC_FP16) ? launch_stem_mma(in1_dev, S, H, W, w.w16, w.bias, po, st)
-                                            : launch_stem(in1_dev, S, H, W, w.w32, w.bias, po, half, st);
+        rc = umma ? launch_stem_mma(in1_dev, S, H, W, w.w16, w.bias, po, x3, st)
+                  : launch_stem(in1_dev, S, H, W, w.w32, w.bias, po, half == ACT_F16, st);
     } else if (!rc) {
         ConvProblem p{};
-        p.in1 = p1; p.in2 = p2; p.gin = g1; p.c2 = cin2; p.k = k; p.stride = stride;
-        p.cout_pad = w.cout_pad; p.w16 = w.w16; p.w32 = w.w32;
+        p.in1 = p1; p.in2 = p2; p.gin = gc; p.c2 = cin2; p.k = k; p.stride = stride;
+        p.cout_pad = w.cout_pad; p.w16 = w.w16; p.w32 = w.w32; p.x3 = x3;
+        p.t1 = t1; p.t2 = t2;
         p.ep.bias = w.bias; p.ep.residual = pr; p.ep.out = po;
         p.ep.out_mode = dense ? OUT_DENSE_F32 : (upsample ? OUT_UPSAMPLE2 : OUT_DENSE);
         p.ep.ldc = go.C; p.ep.cout = cout; p.ep.leaky = d.bn;
@@ -726,11 +789,11 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
         p.ep.drop.seed_lo = (uint32_t)seed; p.ep.drop.seed_hi = (uint32_t)(seed >> 32);
         p.ep.drop.thr16 = (uint32_t)std::lround((double)drop_prob * 65536.0);
         p.ep.drop.keep_scale = 1.0f / (1.0f - drop_prob);
-        rc = (precision == BYOLO_PREC_FP16) ? launch_conv_umma(p, st) : launch_conv_simt(p, half, st);
+        rc = umma ? launch_conv_umma(p, st) : launch_conv_simt(p, half == ACT_F16, st);
     }
     if (!rc) {
         if (dense) {
-            rc = launch_unpack(po, tmp, go, false, st);
+            rc = launch_unpack(po, tmp, go, ACT_F32, st);
             if (!rc && cudaMemcpy2DAsync(out_dev, (size_t)cout * 4, tmp, (size_t)go.C * 4, (size_t)cout * 4, (size_t)S * Ho * Wo,
                                          cudaMemcpyDeviceToDevice, st) != cudaSuccess)
                 rc = -2;
@@ -759,12 +822,12 @@ int byolo_get_activation(byolo_handle h, int32_t conv_index, float* dst_dev, siz
     const size_t n = (size_t)b.g.S * b.g.H * b.g.W * b.valid_c;
     BY_REQUIRE(capacity >= n, "destination too small");
     cudaStream_t st = (cudaStream_t)stream;
-    if (!b.f32) return launch_unpack(b.ptr, dst_dev, b.g, h->act_half(), st);
+    if (!b.f32) return launch_unpack(b.ptr, dst_dev, b.g, h->act_fmt(), st);
     // raw detection map: fp32, stored cout_pad wide -> drop the padding channels
     float* tmp = nullptr;
     const size_t pix = (size_t)b.g.S * b.g.H * b.g.W;
     BY_CUDA(cudaMalloc(&tmp, pix * b.g.C * 4));
-    int rc = launch_unpack(b.ptr, tmp, b.g, false, st);
+    int rc = launch_unpack(b.ptr, tmp, b.g, ACT_F32, st);
     if (!rc && cudaMemcpy2DAsync(dst_dev, (size_t)b.valid_c * 4, tmp, (size_t)b.g.C * 4, (size_t)b.valid_c * 4, pix,
                                  cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         rc = -2;

@@ -23,8 +23,10 @@
 // while the pair tests - phase (A) over the kept list and the rows of the bit matrix in (B), >half of the time at CS = 1 -
 // are split across the cluster and exchanged through distributed shared memory (two cluster barriers per batch).
 #include <algorithm>
-#include <cstdlib>
+#include <array>
+#include <map>
 #include <mutex>
+#include <tuple>
 
 #include <cooperative_groups.h>
 
@@ -262,7 +264,7 @@ __device__ __forceinline__ void scan_candidates(const float* __restrict__ rows, 
 template <int CS>
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float thr, int max_out, int NP,
-           size_t region0, float* __restrict__ out_rows, int* __restrict__ out_idx, int* __restrict__ out_count) {
+           size_t region0, float* __restrict__ out_rows, int* __restrict__ out_idx, int* __restrict__ out_count, int out_img_rows) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cg::cluster_group cluster = cg::this_cluster();
@@ -369,7 +371,10 @@ nms_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float 
 
     // ---- 3. gather ----
     const int n_kept = s_kept;
-    float* orow = out_rows + (size_t)img * max_out * D;
+    // out_img_rows > max_out ("packed" output, the all-gather message of byolo/dist.py): one more row per image whose first
+    // element is the count, so that detections + count travel as ONE fp32 block
+    float* orow = out_rows + (size_t)img * out_img_rows * D;
+    if (out_img_rows > max_out && crank == 0 && tid < D) orow[(size_t)max_out * D + tid] = tid == 0 ? (float)n_kept : 0.f;
     for (int e = crank * kNmsThreads + tid; e < max_out * D; e += kNmsThreads * CS) {      // every CTA holds the full result
         const int k = e / D, c = e - k * D;
         orow[e] = (k < n_kept) ? rows[(size_t)kept_idx[k] * D + c] : 0.f;
@@ -425,7 +430,7 @@ __device__ void bitonic_sort32(uint32_t* key_hi, uint32_t* key_lo, int NP) {
 template <int CS>
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_chunked_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx, float thr, int max_out,
-                   float* __restrict__ out_rows, int* __restrict__ out_idx, int* __restrict__ out_count) {
+                   float* __restrict__ out_rows, int* __restrict__ out_idx, int* __restrict__ out_count, int out_img_rows) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cg::cluster_group cluster = cg::this_cluster();
@@ -544,7 +549,10 @@ nms_chunked_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx
     }
 
     const int n_kept = s_kept;
-    float* orow = out_rows + (size_t)img * max_out * D;
+    // out_img_rows > max_out ("packed" output, the all-gather message of byolo/dist.py): one more row per image whose first
+    // element is the count, so that detections + count travel as ONE fp32 block
+    float* orow = out_rows + (size_t)img * out_img_rows * D;
+    if (out_img_rows > max_out && crank == 0 && tid < D) orow[(size_t)max_out * D + tid] = tid == 0 ? (float)n_kept : 0.f;
     for (int e = crank * kNmsThreads + tid; e < max_out * D; e += kNmsThreads * CS) {
         const int k = e / D, c = e - k * D;
         orow[e] = (k < n_kept) ? rows[(size_t)kept_idx[k] * D + c] : 0.f;
@@ -555,113 +563,83 @@ nms_chunked_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx
     if (CS > 1) cluster.sync();
 }
 
-size_t nms_workspace_bytes(int, int) { return 0; }
-
 int launch_nms(const float* rows, int B, int N, int D, int obj_idx, float iou_thr, int max_out, float* out_rows, int* out_idx,
-               int* out_count, void*, size_t, cudaStream_t st) {
+               int* out_count, const NmsOptions& opt, cudaStream_t st) {
     BY_REQUIRE(N >= 0 && (long long)N * D < (1ll << 31), "NMS: candidate rows must be 32-bit indexable");
     BY_REQUIRE(max_out >= 1 && max_out <= kMaxOut, "max_out must be in [1, 2048]");
     BY_REQUIRE(iou_thr >= 0.f, "iou_thr must be >= 0");
     BY_REQUIRE(obj_idx >= 4 && obj_idx < D, "obj_idx out of range");
+    BY_REQUIRE(opt.force_cs == 0 || opt.force_cs == 1 || opt.force_cs == 2 || opt.force_cs == 4 || opt.force_cs == 8,
+               "cluster size must be 1, 2, 4 or 8");
     if (B == 0) return 0;
-    const bool chunked = N > kMaxN || (getenv("BYOLO_NMS_CHUNKED") && atoi(getenv("BYOLO_NMS_CHUNKED")) == 1);      // tests force it on small N
+    const bool chunked = N > kMaxN || opt.force_chunked;      // tests force it on small N
+    int out_img_rows = max_out + (opt.packed ? 1 : 0);
     int NP = 2;
     while (NP < N) NP <<= 1;
-    const size_t region0 = std::max({(size_t)NP * 4, kAuxBytes, N > 4096 ? (size_t)65536 * 2 : (size_t)0});
+    size_t region0 = std::max({(size_t)NP * 4, kAuxBytes, N > 4096 ? (size_t)65536 * 2 : (size_t)0});
     const size_t smem = chunked ? kChunkSmem : region0 + (size_t)NP * 2;
     BY_REQUIRE(smem <= 227 * 1024 - 1024, "NMS shared memory budget exceeded");
-    // cluster size: as many CTAs per image as keep all images resident at once (148 SMs, one CTA per SM)
-    const int cs_env = getenv("BYOLO_NMS_CS") ? atoi(getenv("BYOLO_NMS_CS")) : 0;      // tests force every cluster size
-    // co-resident clusters of size 1 << i at this smem size: queried once per (device, smem size); the query also opts
-    // the kernels in to the large dynamic shared memory on that device
+    // cluster size: as many CTAs per image as keep all images resident at once (148 SMs, one CTA per SM).
+    // Co-resident clusters of size 1 << i: queried once per (kernel family, device, smem size); the first query on a device
+    // also opts the kernels in to the large dynamic shared memory.
     static std::mutex occ_mutex;
-    static int occ_cache[2][64][4];
-    static size_t occ_smem[2][64] = {};
+    static std::map<std::tuple<int, int, size_t>, std::array<int, 4>> occ_cache;
     int dev = 0;
     BY_CUDA(cudaGetDevice(&dev));
-    BY_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
-    int max_clusters[4];
-    auto launch = [&](auto kernel, int cs) -> cudaError_t {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(B * cs);
+    auto make_cfg = [&](cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int blocks, int cs) {
+        cfg.gridDim = dim3(blocks);
         cfg.blockDim = dim3(kNmsThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = cs;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, kernel, rows, N, D, obj_idx, iou_thr, max_out, NP, region0, out_rows, out_idx, out_count);
     };
-    auto launch_chunked = [&](auto kernel, int cs) -> cudaError_t {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(B * cs);
-        cfg.blockDim = dim3(kNmsThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = cs;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, kernel, rows, N, D, obj_idx, iou_thr, max_out, out_rows, out_idx, out_count);
+    auto kernel_of = [&](int cs) -> const void* {
+        if (chunked)
+            return cs == 8 ? (const void*)nms_chunked_kernel<8> : cs == 4 ? (const void*)nms_chunked_kernel<4>
+                 : cs == 2 ? (const void*)nms_chunked_kernel<2> : (const void*)nms_chunked_kernel<1>;
+        return cs == 8 ? (const void*)nms_kernel<8> : cs == 4 ? (const void*)nms_kernel<4>
+             : cs == 2 ? (const void*)nms_kernel<2> : (const void*)nms_kernel<1>;
     };
-    auto occupancy = [&](auto kernel, int cs) -> int {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess) return 0;
+    auto occupancy = [&](int cs) -> int {
+        if (cudaFuncSetAttribute(kernel_of(cs), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess) return 0;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(cs * 64);
-        cfg.blockDim = dim3(kNmsThreads);
-        cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = cs;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        make_cfg(cfg, attr, cs * 64, cs);
+        cfg.stream = nullptr;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (cudaOccupancyMaxActiveClusters(&n, kernel_of(cs), &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
         return n;
     };
+    std::array<int, 4> max_clusters;
     {
         std::lock_guard<std::mutex> lock(occ_mutex);
-        const int v = chunked ? 1 : 0;
-        if (occ_smem[v][dev] != smem) {
-            if (chunked) {
-                occ_cache[v][dev][0] = occupancy(nms_chunked_kernel<1>, 1);
-                occ_cache[v][dev][1] = occupancy(nms_chunked_kernel<2>, 2);
-                occ_cache[v][dev][2] = occupancy(nms_chunked_kernel<4>, 4);
-                occ_cache[v][dev][3] = occupancy(nms_chunked_kernel<8>, 8);
-            } else {
-                occ_cache[v][dev][0] = occupancy(nms_kernel<1>, 1);
-                occ_cache[v][dev][1] = occupancy(nms_kernel<2>, 2);
-                occ_cache[v][dev][2] = occupancy(nms_kernel<4>, 4);
-                occ_cache[v][dev][3] = occupancy(nms_kernel<8>, 8);
-            }
-            occ_smem[v][dev] = smem;
-        }
-        for (int i = 0; i < 4; ++i) max_clusters[i] = occ_cache[v][dev][i];
+        const auto key = std::make_tuple(chunked ? 1 : 0, dev, smem);
+        auto it = occ_cache.find(key);
+        if (it == occ_cache.end())
+            it = occ_cache.emplace(key, std::array<int, 4>{occupancy(1), occupancy(2), occupancy(4), occupancy(8)}).first;
+        max_clusters = it->second;
     }
     int cs = 1;
     for (int i = 3; i >= 1; --i)
         if (max_clusters[i] >= B) { cs = 1 << i; break; }
-    if (cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8) cs = cs_env;
-    cudaError_t err;
+    if (opt.force_cs) cs = opt.force_cs;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    make_cfg(cfg, attr, B * cs, cs);
     if (chunked) {
-        if (cs == 8) err = launch_chunked(nms_chunked_kernel<8>, 8);
-        else if (cs == 4) err = launch_chunked(nms_chunked_kernel<4>, 4);
-        else if (cs == 2) err = launch_chunked(nms_chunked_kernel<2>, 2);
-        else err = launch_chunked(nms_chunked_kernel<1>, 1);
-    } else if (cs == 8) err = launch(nms_kernel<8>, 8);
-    else if (cs == 4) err = launch(nms_kernel<4>, 4);
-    else if (cs == 2) err = launch(nms_kernel<2>, 2);
-    else err = launch(nms_kernel<1>, 1);
-    BY_CUDA(err);
+        void* args[] = {(void*)&rows, (void*)&N, (void*)&D, (void*)&obj_idx, (void*)&iou_thr, (void*)&max_out,
+                        (void*)&out_rows, (void*)&out_idx, (void*)&out_count, (void*)&out_img_rows};
+        BY_CUDA(cudaLaunchKernelExC(&cfg, kernel_of(cs), args));
+    } else {
+        void* args[] = {(void*)&rows, (void*)&N, (void*)&D, (void*)&obj_idx, (void*)&iou_thr, (void*)&max_out, (void*)&NP,
+                        (void*)&region0, (void*)&out_rows, (void*)&out_idx, (void*)&out_count, (void*)&out_img_rows};
+        BY_CUDA(cudaLaunchKernelExC(&cfg, kernel_of(cs), args));
+    }
     BY_CUDA(cudaGetLastError());
     return 0;
 }

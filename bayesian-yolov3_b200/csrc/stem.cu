@@ -31,26 +31,32 @@ __device__ __forceinline__ uint32_t pack2(__half lo, __half hi) {
 }
 }  // namespace
 
-__global__ void __launch_bounds__(kWarps * 32, 4)
-stem_mma_kernel(const float* __restrict__ img, int H, int W, int num_tiles, const __half* __restrict__ w16 /*[32][27]*/,
+// X3 (split-fp16 mode): image and weights are hi + lo fp16 pairs, three MMAs (hi*hi + hi*lo + lo*hi) per K step, and the
+// output pixel is stored as [hi 32 halves | lo 32 halves].
+template <bool X3>
+__global__ void __launch_bounds__(kWarps * 32, X3 ? 2 : 4)
+stem_mma_kernel(const float* __restrict__ img, int H, int W, int num_tiles, const __half* __restrict__ w16 /*[32 (+32 lo)][27]*/,
                 const float* __restrict__ bias, __half* __restrict__ out) {
-    __shared__ __align__(16) __half sin[(kTH + 2) * kPitch];
-    __shared__ __align__(16) __half sout[kWarps][16 * kOutPitch];
+    constexpr int NP = X3 ? 2 : 1;
+    __shared__ __align__(16) __half sin[NP][(kTH + 2) * kPitch];
+    __shared__ __align__(16) __half sout[kWarps][NP][16 * kOutPitch];
     const int tiles_x = W / kTW, tiles_y = H / kTH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 
     // B fragments (weights): b[s][nt] = {W[n = nt*8+g][k = s*16 + 2t, +1], W[n][k + 8, + 9]}, zero for k >= 27
-    uint32_t bf[2][4][2];
+    uint32_t bf[NP][2][4][2];
+#pragma unroll
+    for (int pl = 0; pl < NP; ++pl)
 #pragma unroll
     for (int s = 0; s < 2; ++s)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
-                const int k = s * 16 + p * 8 + 2 * t, n = nt * 8 + g;
+                const int k = s * 16 + p * 8 + 2 * t, n = nt * 8 + g + 32 * pl;
                 const __half lo = k < 27 ? w16[n * 27 + k] : __float2half(0.f);
                 const __half hi = k + 1 < 27 ? w16[n * 27 + k + 1] : __float2half(0.f);
-                bf[s][nt][p] = pack2(lo, hi);
+                bf[pl][s][nt][p] = pack2(lo, hi);
             }
     float bs[4][2];
 #pragma unroll
@@ -80,30 +86,40 @@ stem_mma_kernel(const float* __restrict__ img, int H, int W, int num_tiles, cons
         float v = 0.f;
         if (c < kInW && iy >= 0 && iy < H && ix >= 0 && ix < W)
             v = __ldg(img + ((long long)(b * H + iy) * W + (x0 - 1)) * 3 + c);
-        sin[i] = __float2half_rn(v);
+        const __half hi = __float2half_rn(v);
+        sin[0][i] = hi;
+        if constexpr (X3) sin[1][i] = __float2half_rn(v - __half2float(hi));
     }
     __syncthreads();
 
-    __half* so = sout[warp];
 #pragma unroll 1
     for (int mt = 0; mt < 4; ++mt) {                     // warp: rows 2*warp, 2*warp+1; two 16-pixel tiles per row
         const int ly = 2 * warp + (mt >> 1), lx = (mt & 1) * 16;
-        const __half* p0 = sin + ly * kPitch + (lx + g) * 3;      // pixel g of the tile; pixel g+8 is 24 halves further
-        uint32_t a[2][4];
+        uint32_t a[NP][2][4];
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int pl = 0; pl < NP; ++pl) {
+            const __half* p0 = sin[pl] + ly * kPitch + (lx + g) * 3;      // pixel g of the tile; pixel g+8 is 24 halves further
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                a[s][2 * p] = pack2(p0[koff[s][p][0]], p0[koff[s][p][1]]);
-                a[s][2 * p + 1] = pack2(p0[24 + koff[s][p][0]], p0[24 + koff[s][p][1]]);
-            }
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    a[pl][s][2 * p] = pack2(p0[koff[s][p][0]], p0[koff[s][p][1]]);
+                    a[pl][s][2 * p + 1] = pack2(p0[24 + koff[s][p][0]], p0[24 + koff[s][p][1]]);
+                }
+        }
         float acc[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
-            mma16816(acc[nt], a[0], bf[0][nt][0], bf[0][nt][1]);
-            mma16816(acc[nt], a[1], bf[1][nt][0], bf[1][nt][1]);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                mma16816(acc[nt], a[0][s], bf[0][s][nt][0], bf[0][s][nt][1]);
+                if constexpr (X3) {
+                    mma16816(acc[nt], a[0][s], bf[1][s][nt][0], bf[1][s][nt][1]);     // hi * lo
+                    mma16816(acc[nt], a[1][s], bf[0][s][nt][0], bf[0][s][nt][1]);     // lo * hi
+                }
+            }
         }
         __syncwarp();                                    // the previous tile has left the staging block
 #pragma unroll
@@ -112,29 +128,38 @@ stem_mma_kernel(const float* __restrict__ img, int H, int W, int num_tiles, cons
             float v2 = acc[nt][2] + bs[nt][0], v3 = acc[nt][3] + bs[nt][1];
             v0 = fmaxf(v0, 0.1f * v0); v1 = fmaxf(v1, 0.1f * v1);
             v2 = fmaxf(v2, 0.1f * v2); v3 = fmaxf(v3, 0.1f * v3);
-            *reinterpret_cast<__half2*>(so + g * kOutPitch + nt * 8 + 2 * t) = __floats2half2_rn(v0, v1);
-            *reinterpret_cast<__half2*>(so + (g + 8) * kOutPitch + nt * 8 + 2 * t) = __floats2half2_rn(v2, v3);
+            const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+            *reinterpret_cast<__half2*>(sout[warp][0] + g * kOutPitch + nt * 8 + 2 * t) = h01;
+            *reinterpret_cast<__half2*>(sout[warp][0] + (g + 8) * kOutPitch + nt * 8 + 2 * t) = h23;
+            if constexpr (X3) {
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                *reinterpret_cast<__half2*>(sout[warp][1] + g * kOutPitch + nt * 8 + 2 * t) = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
+                *reinterpret_cast<__half2*>(sout[warp][1] + (g + 8) * kOutPitch + nt * 8 + 2 * t) = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+            }
         }
         __syncwarp();
-        // 16 pixels x 64 B, contiguous in the output row
-        __half* o = out + (((long long)b * H + (y0 + ly)) * W + (x0 + lx)) * 32;
+        // 16 pixels x 64 B (x2 in split mode: [hi | lo] per pixel), contiguous in the output row
+        __half* o = out + (((long long)b * H + (y0 + ly)) * W + (x0 + lx)) * (32 * NP);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int idx = lane + 32 * j, row = idx >> 2, q = idx & 3;
-            const uint4 v = *reinterpret_cast<const uint4*>(so + row * kOutPitch + q * 8);
-            *reinterpret_cast<uint4*>(o + row * 32 + q * 8) = v;
+        for (int j = 0; j < 2 * NP; ++j) {
+            const int idx = lane + 32 * j, row = idx / (4 * NP), q = idx % (4 * NP), pl = q >> 2;
+            const uint4 v = *reinterpret_cast<const uint4*>(sout[warp][pl] + row * kOutPitch + (q & 3) * 8);
+            *reinterpret_cast<uint4*>(o + row * 32 * NP + q * 8) = v;
         }
     }
     __syncthreads();                                     // everyone is done with the halo tile before it is overwritten
   }
 }
 
-int launch_stem_mma(const float* img, int B, int H, int W, const __half* w16, const float* bias, void* out, cudaStream_t st) {
+int launch_stem_mma(const float* img, int B, int H, int W, const __half* w16, const float* bias, void* out, bool x3, cudaStream_t st) {
     BY_REQUIRE(H % kTH == 0 && W % kTW == 0, "stem: image size must be a multiple of 32");
     const long long tiles = (long long)B * (H / kTH) * (W / kTW);
     BY_REQUIRE(tiles < (1ll << 31), "stem: too many tiles");
-    const int grid = (int)std::min<long long>(tiles, 148 * 4);          // 4 resident CTAs per SM, each walks its tiles
-    stem_mma_kernel<<<grid, kWarps * 32, 0, st>>>(img, H, W, (int)tiles, w16, bias, (__half*)out);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<long long>(tiles, (long long)sms * (x3 ? 2 : 4));   // resident CTAs per SM, each walks its tiles
+    if (x3) stem_mma_kernel<true><<<grid, kWarps * 32, 0, st>>>(img, H, W, (int)tiles, w16, bias, (__half*)out);
+    else stem_mma_kernel<false><<<grid, kWarps * 32, 0, st>>>(img, H, W, (int)tiles, w16, bias, (__half*)out);
     BY_CUDA(cudaGetLastError());
     return 0;
 }

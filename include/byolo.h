@@ -26,7 +26,10 @@ enum { BYOLO_STANDARD = 0, BYOLO_ALEATORIC = 1, BYOLO_EPISTEMIC = 2 };   /* yolo
 enum {
     BYOLO_PREC_FP32 = 0,        /* CUDA-core fp32 convs, fp32 activations: the exact reference-precision path      */
     BYOLO_PREC_FP16_SIMT = 1,   /* CUDA-core convs on fp16-stored activations (debug twin of the tensor-core path) */
-    BYOLO_PREC_FP16 = 2         /* tcgen05 tensor-core convs, fp16 operands, fp32 accumulate (product path)        */
+    BYOLO_PREC_FP16 = 2,        /* tcgen05 tensor-core convs, fp16 operands, fp32 accumulate (fastest path)        */
+    BYOLO_PREC_FP16X3 = 3       /* tcgen05 split-fp16: every operand a hi+lo fp16 pair, hi*hi + hi*lo + lo*hi into one
+                                   fp32 accumulator (3 MMAs per K step) - fp32-grade results, meets the 1e-3 parity
+                                   bound element-wise (tests/test_gpu_fullsize.py)                                 */
 };
 
 typedef struct byolo_config {
@@ -41,7 +44,7 @@ typedef struct byolo_config {
     float prior_h[9], prior_w[9]; /* config['priors'] as fractions of the image, stride 32 first (yolov3.py:29-61) */
 } byolo_config;
 
-/* Returns the ABI version (1). */
+/* Returns the ABI version (2: byolo_conv_layer takes t1 / t2, BYOLO_PREC_FP16X3, count row in gathered detections). */
 int byolo_version(void);
 const char* byolo_last_error(void);
 
@@ -72,11 +75,24 @@ int byolo_forward(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed
 int byolo_nms(const float* rows_dev, int32_t B, int32_t N, int32_t D, int32_t obj_idx, float iou_thr, int32_t max_out,
               float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev, void* stream);
 
+/* byolo_nms with the options the tests and the multi-GPU gather need.  packed != 0: out_rows_dev is [B, max_out + 1, D] and
+ * row max_out of every image holds (count, 0, ...) - detections and count leave as ONE fp32 block, the message of the
+ * single all-gather of SURVEY.md 8e (out_count_dev may then be NULL).  force_cluster_size (0 = automatic | 1 | 2 | 4 | 8)
+ * and force_chunked (the N > 32768 path for any N) are test hooks: results are identical for every setting. */
+int byolo_nms_ex(const float* rows_dev, int32_t B, int32_t N, int32_t D, int32_t obj_idx, float iou_thr, int32_t max_out,
+                 float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev, int32_t packed, int32_t force_cluster_size,
+                 int32_t force_chunked, void* stream);
+
 /* forward + nms on device buffers (what Inference.nms fetches, inference_epistemic.py:50-54). rows_dev may be NULL
  * (internal scratch is used). */
 int byolo_detect(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
                  int32_t max_out, float* rows_dev, float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev,
                  void* stream);
+
+/* byolo_detect writing the packed layout of byolo_nms_ex: out_packed_dev [B, max_out + 1, D].  What each rank of the
+ * image-sharded multi-GPU path hands to ncclAllGather (byolo/dist.py) - no packing kernels or host work in between. */
+int byolo_detect_packed(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
+                        int32_t max_out, float* out_packed_dev, int32_t* out_idx_dev, void* stream);
 
 /* The call a user of the reference makes (detect.py:124 `sess.run(box_op, {img_tensor: img})`): HOST buffers in and
  * out; copies the images host->device, runs byolo_detect, copies results back and synchronises `stream`.
@@ -101,12 +117,14 @@ int byolo_decode(byolo_handle h, const float* raw0_dev, const float* raw1_dev, c
  * arrays, run through the chosen precision path.  in2 (channel concat partner, 1x1 only) and residual may be NULL.
  * kernel HWIO [k,k,cin1+cin2,cout]; bn = {beta,gamma,mean,var}[cout] or NULL with bias[cout] (linear, no leaky).
  * upsample: store with the nearest x2 of layers.py:578-580 ([S,2H,2W,cout]).  dropout_layer < 0: no dropout.
- * cin1 == 3 selects the stem kernels (darknet.py:10: 3x3, stride 1, 32 filters, BN; H, W multiples of 32). */
+ * cin1 == 3 selects the stem kernels (darknet.py:10: 3x3, stride 1, 32 filters, BN; H, W multiples of 32).
+ * t1 / t2 > 1 (1x1 convs only): stack_feature_map without the copy (layers.py:595-597) - in1 (t1, no in2) or in2 (t2) holds
+ * S / t samples and sample s of the conv reads sample s / t of it; pass 1 otherwise. */
 int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_dev, int32_t S, int32_t H, int32_t W,
                      int32_t cin1, int32_t cin2, int32_t k, int32_t stride, int32_t cout, const float* kernel_host,
                      const float* bn_host, const float* bias_host, const float* residual_dev, int32_t upsample,
                      int32_t dropout_layer, int32_t T, uint64_t seed, int32_t image_index0, float drop_prob,
-                     float* out_dev, void* stream);
+                     int32_t t1, int32_t t2, float* out_dev, void* stream);
 
 /* Debug read-back of ModelBuilder layer outputs (model.py:40-41 `layers` list semantics): conv index 0..74 in weight
  * order; writes dense fp32 [S,H,W,C] to dst_dev (capacity in floats) and reports the shape.  Valid after a forward. */

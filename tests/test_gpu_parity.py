@@ -7,6 +7,7 @@ import pytest
 import torch
 
 import golden_inputs as GI
+from golden_inputs import stress_rows
 from byolo import priors as P
 from byolo import weights as W
 from oracle import decode as D
@@ -36,10 +37,11 @@ def assert_close(a, b, rtol, atol, what):
 
 
 # ------------------------------------------------------------------------------------------------------ K3: NMS
-def _nms_gpu(rows, obj_idx, max_out=1000):
+def _nms_gpu(rows, obj_idx, max_out=1000, cluster=0, chunked=False):
+    """cluster / chunked: byolo_nms_ex test hooks (CTAs per image, the N > 32768 kernel for any N)."""
     import byolo
     r = torch.from_numpy(np.ascontiguousarray(rows, np.float32)).cuda()
-    boxes, cnt, idx = byolo.nms(r, obj_idx, max_out)
+    boxes, cnt, idx = byolo.nms(r, obj_idx, max_out, cluster=cluster, chunked=chunked)
     torch.cuda.synchronize()
     return boxes.cpu().numpy(), cnt.cpu().numpy(), idx.cpu().numpy()
 
@@ -53,48 +55,11 @@ def test_nms_bit_exact_on_reference_rows(name):
     assert np.array_equal(boxes, g['nms_rows'])            # padded with zeros beyond count
 
 
-def stress_rows(B, seed, N=22743, D=23, obj_idx=14, img=608):
-    """NMS stress rows in reference order: cell-centred boxes, 5% exact score ties,
-    200 planted clusters of 30 heavily overlapping boxes."""
-    rng = np.random.default_rng(seed)
-    pri = np.array([p for s in PRI for p in s])
-    rows = np.zeros((B, N, D), np.float32)
-    off = 0
-    for j, stride in enumerate((32, 16, 8)):
-        g = img // stride
-        for p in range(3):
-            n = g * g
-            yy, xx = np.meshgrid(np.arange(g), np.arange(g), indexing='ij')
-            cy = (yy.reshape(-1) + 0.5 + rng.uniform(-.5, .5, (B, n))) / g
-            cx = (xx.reshape(-1) + 0.5 + rng.uniform(-.5, .5, (B, n))) / g
-            h = pri[j * 3 + p, 0] * rng.lognormal(0, .5, (B, n))
-            w = pri[j * 3 + p, 1] * rng.lognormal(0, .5, (B, n))
-            rows[:, off:off + n, 0] = cy - h / 2
-            rows[:, off:off + n, 1] = cx - w / 2
-            rows[:, off:off + n, 2] = cy + h / 2
-            rows[:, off:off + n, 3] = cx + w / 2
-            off += n
-    rows[:, :, obj_idx] = 1 / (1 + np.exp(-rng.normal(-2, 2, (B, N))))
-    rows[:, :, 4:obj_idx] = rng.random((B, N, obj_idx - 4))
-    for b in range(B):
-        tie = rng.choice(N, N // 20, replace=False)
-        rows[b, tie[: len(tie) // 2], obj_idx] = rows[b, tie[len(tie) // 2: 2 * (len(tie) // 2)], obj_idx]
-        for c in rng.choice(N, 200, replace=False):
-            members = rng.choice(N, 30, replace=False)
-            rows[b, members, :4] = rows[b, c, :4] + rng.normal(0, 0.002, (30, 4)).astype(np.float32)
-            rows[b, members, obj_idx] = np.clip(rows[b, c, obj_idx] + rng.normal(0, .05, 30), 1e-4, 1 - 1e-4)
-    return rows
-
-
 @pytest.mark.parametrize('cluster', [0, 1, 2, 4, 8])
-def test_nms_stress_full_size_bit_exact(cluster, monkeypatch):
+def test_nms_stress_full_size_bit_exact(cluster):
     """cluster = CTAs per image (0: the library's own choice); every split of the pair tests must select the same boxes."""
-    if cluster:
-        monkeypatch.setenv('BYOLO_NMS_CS', str(cluster))
-    else:
-        monkeypatch.delenv('BYOLO_NMS_CS', raising=False)
     rows = stress_rows(4, 105)
-    boxes, cnt, idx = _nms_gpu(rows, 14)
+    boxes, cnt, idx = _nms_gpu(rows, 14, cluster=cluster)
     for b in range(rows.shape[0]):
         want = ONMS.nms(rows[b], 14)
         assert cnt[b] == len(want)
@@ -102,6 +67,23 @@ def test_nms_stress_full_size_bit_exact(cluster, monkeypatch):
         assert np.array_equal(boxes[b, :cnt[b]], rows[b][want])
         assert np.all(idx[b, cnt[b]:] == -1) and np.all(boxes[b, cnt[b]:] == 0)
     assert cnt.min() == 1000                                    # generator guarantees >= 1000 survivors
+
+
+def test_nms_packed_output_carries_the_count_row():
+    """byolo_nms_ex(packed): [B, max_out + 1, D] with (count, 0, ...) in the extra row - the all-gather message."""
+    import byolo
+    rows = stress_rows(3, 107)
+    rows[2, :, 14] = 0.5
+    rows[2, :, :4] = [0.1, 0.1, 0.5, 0.5]                       # one survivor: the count row must say 1
+    r = torch.from_numpy(rows).cuda()
+    boxes, cnt, idx = byolo.nms(r, 14, 1000)
+    packed, idx2 = byolo.nms(r, 14, 1000, packed=True)
+    torch.cuda.synchronize()
+    packed = packed.cpu().numpy()
+    assert packed.shape == (3, 1001, 23)
+    assert np.array_equal(packed[:, :1000], boxes.cpu().numpy()) and np.array_equal(idx2.cpu().numpy(), idx.cpu().numpy())
+    assert np.array_equal(packed[:, 1000, 0].astype(np.int32), cnt.cpu().numpy()) and np.all(packed[:, 1000, 1:] == 0)
+    assert packed[2, 1000, 0] == 1
 
 
 def _random_rows(B, N, D, obj_idx, seed, tie_frac=0.05):
@@ -120,13 +102,11 @@ def _random_rows(B, N, D, obj_idx, seed, tie_frac=0.05):
 
 
 @pytest.mark.parametrize('cluster', [1, 8])
-def test_nms_chunked_kernel_on_stress_rows(cluster, monkeypatch):
+def test_nms_chunked_kernel_on_stress_rows(cluster):
     """The chunked kernel (score-ordered chunks of <= 4096 candidates, used for N > 32768) forced onto the 22743-row stress
     case: same selection as the oracle."""
-    monkeypatch.setenv('BYOLO_NMS_CHUNKED', '1')
-    monkeypatch.setenv('BYOLO_NMS_CS', str(cluster))
     rows = stress_rows(2, 106)
-    boxes, cnt, idx = _nms_gpu(rows, 14)
+    boxes, cnt, idx = _nms_gpu(rows, 14, cluster=cluster, chunked=True)
     for b in range(rows.shape[0]):
         want = ONMS.nms(rows[b], 14)
         assert cnt[b] == len(want) and np.array_equal(idx[b, :cnt[b]], want), 'image %d' % b
@@ -155,18 +135,16 @@ def _tie_rows():
     return rows
 
 
-def test_nms_chunked_with_more_ties_than_a_chunk(monkeypatch):
-    monkeypatch.setenv('BYOLO_NMS_CHUNKED', '1')
+def test_nms_chunked_with_more_ties_than_a_chunk():
     rows = _tie_rows()
-    boxes, cnt, idx = _nms_gpu(rows, 4, max_out=2000)
+    boxes, cnt, idx = _nms_gpu(rows, 4, max_out=2000, chunked=True)
     want = ONMS.nms(rows[0], 4, 2000)
     assert cnt[0] == len(want) == 2000 and np.array_equal(idx[0, :cnt[0]], want)
     assert 0 < (want < 10000).sum() <= 500 and (want >= 10000).sum() >= 1500
 
 
 @pytest.mark.parametrize('cluster', [1, 8])
-def test_nms_edge_cases(cluster, monkeypatch):
-    monkeypatch.setenv('BYOLO_NMS_CS', str(cluster))
+def test_nms_edge_cases(cluster):
     rng = np.random.default_rng(5)
     # all boxes identical -> 1 survivor; zero-area boxes never suppress; tiny N; max_out smaller than survivors
     rows = np.zeros((3, 70, 7), np.float32)
@@ -177,7 +155,7 @@ def test_nms_edge_cases(cluster, monkeypatch):
     rows[2, :, :2] = rng.random((70, 2))
     rows[2, :, 2:4] = rows[2, :, :2] + 0.01
     rows[2, :, 4] = rng.random(70)
-    boxes, cnt, idx = _nms_gpu(rows, 4, max_out=50)
+    boxes, cnt, idx = _nms_gpu(rows, 4, max_out=50, cluster=cluster)
     for b in range(3):
         want = ONMS.nms(rows[b], 4, 50)
         assert cnt[b] == len(want) and np.array_equal(idx[b, :cnt[b]], want)
@@ -209,10 +187,16 @@ def test_decode_on_reference_raw_outputs(name):
 
 
 # ------------------------------------------------------------------------------------------------------ K1: conv layers
-def ref_conv(x, kernel, bn=None, bias=None, x2=None, residual=None, stride=1, upsample=False, drop=None, emulate=False):
+def ref_conv(x, kernel, bn=None, bias=None, x2=None, residual=None, stride=1, upsample=False, drop=None, emulate=False,
+             t1=1, t2=1):
     """Oracle for byolo_conv_layer: torch CPU fp32 conv with the engine's folding; emulate=True rounds the operands
-    (and the stored fp16 output) exactly where the fp16 paths round them."""
+    (and the stored fp16 output) exactly where the fp16 paths round them.  t1 / t2: stack_feature_map of x / x2
+    (tf.concat([x]*T, axis=0) per image, layers.py:595-597: sample s reads sample s // t)."""
     rd = (lambda t: t.half().float()) if emulate else (lambda t: t)
+    if t1 > 1:
+        x = np.repeat(x, t1, axis=0)
+    if t2 > 1:
+        x2 = np.repeat(x2, t2, axis=0)
     xin = torch.from_numpy(x if x2 is None else np.concatenate([x, x2], -1)).permute(0, 3, 1, 2)
     k = torch.from_numpy(kernel).permute(3, 2, 0, 1)
     if bn is not None:
@@ -259,15 +243,27 @@ CONV_CASES = {
     'det_42': (4, 12, 20, 256, 0, 1, 1, 42, False, False, False, True),
     'det_21': (2, 5, 3, 1024, 0, 1, 1, 21, False, False, False, True),
 }
+# MC-stacked sources (A_STACK1 / A_STACK2): name -> (conv case fields..., t1, t2); S is the number of samples the conv sees
+STACK_CASES = {
+    'stack1_1024_512_drop': ((6, 7, 5, 1024, 0, 1, 1, 512, False, False, True, False), 3, 1),     # conv "75": in1 = L74 of S/3 images
+    'stack1_256_128': ((4, 9, 11, 256, 0, 1, 1, 128, False, False, False, False), 2, 1),
+    'stack2_cat_256_512_drop': ((6, 10, 6, 256, 512, 1, 1, 256, False, False, True, False), 1, 3),  # conv "87": [upsampled, L61 stacked]
+    'stack2_cat_128_256': ((8, 12, 20, 128, 256, 1, 1, 128, False, False, False, False), 1, 4),     # conv "99"
+}
 
 
 def _conv_case(name):
-    S, H, Wd, c1, c2, k, stride, cout, res, up, drop, dense = CONV_CASES[name]
-    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
-    x = rng.standard_normal((S, H, Wd, c1)).astype(np.float32)
+    t1 = t2 = 1
+    if name in STACK_CASES:
+        (S, H, Wd, c1, c2, k, stride, cout, res, up, drop, dense), t1, t2 = STACK_CASES[name]
+    else:
+        S, H, Wd, c1, c2, k, stride, cout, res, up, drop, dense = CONV_CASES[name]
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    x = rng.standard_normal((S // t1, H, Wd, c1)).astype(np.float32)
     if c1 == 3:
         x = rng.random((S, H, Wd, 3), dtype=np.float32)          # the stem reads images in [0,1) (dataset_utils.py:6-11)
-    x2 = rng.standard_normal((S, H, Wd, c2)).astype(np.float32) if c2 else None
+    x2 = rng.standard_normal((S // t2, H, Wd, c2)).astype(np.float32) if c2 else None
     cin = c1 + c2
     kernel = (rng.standard_normal((k, k, cin, cout)) * np.sqrt(2.0 / (k * k * cin))).astype(np.float32)
     bn = bias = None
@@ -277,8 +273,9 @@ def _conv_case(name):
         bn = dict(beta=(rng.standard_normal(cout) * .1).astype(np.float32), gamma=rng.uniform(.8, 1.2, cout).astype(np.float32),
                   mean=(rng.standard_normal(cout) * .1).astype(np.float32), var=rng.uniform(.5, 1.5, cout).astype(np.float32))
     residual = rng.standard_normal((S, H // stride, Wd // stride, cout)).astype(np.float32) if res else None
-    dropspec = (77, 3, 2, 5, 0.1) if drop else None          # seed, layer id, T, image0, p
-    return dict(x=x, x2=x2, kernel=kernel, bn=bn, bias=bias, residual=residual, stride=stride, upsample=up, drop=dropspec)
+    dropspec = (77, 3, max(t1, t2, 2), 5, 0.1) if drop else None          # seed, layer id, T, image0, p
+    return dict(x=x, x2=x2, kernel=kernel, bn=bn, bias=bias, residual=residual, stride=stride, upsample=up, drop=dropspec,
+                t1=t1, t2=t2)
 
 
 def _run_conv(c, precision):
@@ -288,29 +285,44 @@ def _run_conv(c, precision):
     out = byolo.conv_layer(t(c['x']), c['kernel'], bn=c['bn'], bias=c['bias'], x2=t(c['x2']), residual=t(c['residual']),
                            stride=c['stride'], upsample=c['upsample'], precision=precision,
                            dropout_layer=d[1] if d else -1, T=d[2] if d else 1, seed=d[0] if d else 0,
-                           image_index0=d[3] if d else 0, drop_prob=d[4] if d else 0.1)
+                           image_index0=d[3] if d else 0, drop_prob=d[4] if d else 0.1, t1=c['t1'], t2=c['t2'])
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
 
-@pytest.mark.parametrize('name', list(CONV_CASES))
+def _ref(c, emulate=False):
+    return ref_conv(c['x'], c['kernel'], c['bn'], c['bias'], c['x2'], c['residual'], c['stride'], c['upsample'], c['drop'],
+                    emulate=emulate, t1=c['t1'], t2=c['t2'])
+
+
+@pytest.mark.parametrize('name', list(CONV_CASES) + list(STACK_CASES))
 def test_conv_fp32_cuda_core_path(name):
     """Exact path: fp32 operands and activations; tolerance 1e-4 (summation order only)."""
     c = _conv_case(name)
     got = _run_conv(c, 'fp32')
-    want = ref_conv(c['x'], c['kernel'], c['bn'], c['bias'], c['x2'], c['residual'], c['stride'], c['upsample'], c['drop'])
+    want = _ref(c)
     assert got.shape == want.shape
     assert_close(got, want, 1e-4, 1e-4, name)
 
 
-@pytest.mark.parametrize('name', list(CONV_CASES))
+@pytest.mark.parametrize('name', list(CONV_CASES) + list(STACK_CASES))
+def test_conv_split_fp16_tensor_core_path(name):
+    """tcgen05 split-fp16 mode (hi*hi + hi*lo + lo*hi, fp32 accumulate, activations stored as hi + lo pairs) vs the
+    plain fp32 oracle: the same tolerance as the fp32 CUDA-core path (summation order only)."""
+    c = _conv_case(name)
+    got = _run_conv(c, 'fp16x3')
+    want = _ref(c)
+    assert got.shape == want.shape
+    assert_close(got, want, 1e-4, 1e-4, name)
+
+
+@pytest.mark.parametrize('name', list(CONV_CASES) + list(STACK_CASES))
 def test_conv_fp16_tensor_core_path(name):
     """tcgen05 path vs the oracle with operands rounded to fp16 where the kernel rounds them.  fp16 outputs may differ
     by one fp16 ulp (2^-10 relative) where the fp32 sums straddle a rounding boundary: rtol 2e-3, atol 2e-3."""
     c = _conv_case(name)
     got = _run_conv(c, 'fp16')
-    want = ref_conv(c['x'], c['kernel'], c['bn'], c['bias'], c['x2'], c['residual'], c['stride'], c['upsample'], c['drop'],
-                    emulate=True)
+    want = _ref(c, emulate=True)
     assert got.shape == want.shape
     assert_close(got, want, 2e-3, 2e-3, name)
     simt = _run_conv(c, 'fp16-simt')                        # CUDA-core twin with identical rounding points
@@ -356,12 +368,14 @@ def _first_bad_layer(eng, res, case, rtol, atol):
     return '; '.join(msgs) if msgs else 'all conv outputs within tolerance'
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'fp16x3'])
 @pytest.mark.parametrize('name', list(GI.CASES))
-def test_forward_fp32_matches_reference_graph(name):
-    """Whole path in the exact precision mode vs the golden rows produced by the reference's own graph code.
-    Tolerance: the north-star 1e-3 relative (observed ~1e-5), absolute floors for cancellation columns."""
+def test_forward_matches_reference_graph(name, precision):
+    """Whole path in the exact precision modes - fp32 CUDA cores, and the split-fp16 tensor-core mode - vs the golden rows
+    produced by the reference's own graph code.  Tolerance: the north-star 1e-3 relative (observed ~1e-5), absolute
+    floors for cancellation columns."""
     case, g = GI.CASES[name], np.load(os.path.join(G, name + '.npz'))
-    eng = _engine_for(case, 'fp32')
+    eng = _engine_for(case, precision)
     img = torch.from_numpy(GI.images(case)).cuda()
     boxes, cnt, idx, rows = eng.detect(img, seed=case.get('dropout_seed', 0), want_rows=True)
     torch.cuda.synchronize()

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.lib().byolo_version() == 1
+    assert _lib.lib().byolo_version() == 2
 
 
 def test_no_cpu_fallback_and_argument_errors():
@@ -155,21 +155,25 @@ def _gloo_worker(rank, world, port, n_images, ret):
     sys.path[:0] = [os.path.join(ROOT, 'bayesian-yolov3_b200')]
     from byolo import dist as bd
     dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    max_out, D = 5, 3
 
-    def run_local(imgs, index0):                     # stub hot path: result depends only on the GLOBAL image index
-        b = imgs.shape[0]
-        boxes = torch.zeros((b, 5, 3))
-        cnt = torch.zeros((b,), dtype=torch.int32)
-        for i in range(b):
+    def run_packed(imgs, index0, out):               # stub hot path: the packed block depends only on the GLOBAL image index
+        out.zero_()
+        for i in range(imgs.shape[0]):
             g = index0 + i
-            cnt[i] = g % 5 + 1
-            boxes[i, :cnt[i]] = float(g) + imgs[i].sum()
-        return boxes, cnt
+            cnt = g % 5 + 1
+            out[i, :cnt] = float(g) + imgs[i].sum()
+            out[i, max_out, 0] = cnt
 
     imgs = torch.arange(n_images, dtype=torch.float32).view(n_images, 1, 1, 1).expand(n_images, 2, 2, 3).contiguous()
-    boxes, cnt = bd.ShardedDetector(run_local).detect(imgs)
-    single_b, single_c = run_local(imgs, 0)
-    ok = torch.equal(boxes, single_b) and torch.equal(cnt, single_c)
+    sd = bd.ShardedDetector(run_packed, n_images, D, max_out=max_out)
+    single = torch.zeros((n_images, max_out + 1, D))
+    run_packed(imgs, 0, single)
+    ok = True
+    for slot in (0, 1, 0):                            # slots are reusable; results are views of the slot's receive buffer
+        got = sd.result(sd.submit(imgs, slot))
+        ok = ok and torch.equal(got.boxes, single[:, :max_out]) and torch.equal(got.counts, single[:, max_out, 0])
+        ok = ok and got.counts_int().dtype == torch.int32 and got.boxes.shape == (n_images, max_out, D)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

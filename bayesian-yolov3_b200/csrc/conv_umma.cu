@@ -243,12 +243,13 @@ constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;
+constexpr int kChunkStride = 128;      // split mode: N tile <= 128 columns, four chunk buffers
 
 struct SmemCtl {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
-    uint64_t acc_full[2];
-    uint64_t acc_empty[2];
+    uint64_t acc_full[4];       // fp16 mode: two 256-column accumulators; split mode: four 128-column chunk buffers
+    uint64_t acc_empty[4];
     uint32_t tmem_base;
     uint32_t pad[3];
     alignas(16) float bias[kMaxBias];      // read as float4 by the epilogue
@@ -405,10 +406,10 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
         float sums[kSums][CH];
         if constexpr (X3) {
             for (int c = 0; c < p.chunks_per_tile; ++c, ++chunk_it) {
-                const uint32_t cas = chunk_it & 1, cphase = (chunk_it >> 1) & 1;
+                const uint32_t cas = chunk_it & 3, cphase = (chunk_it >> 2) & 1;
                 mbar_wait(acc_full0 + 8 * cas, cphase);
                 tc_fence_after();
-                const uint32_t ctaddr = tmem_base + cas * kAccStride + ((uint32_t)(quad * 32) << 16);
+                const uint32_t ctaddr = tmem_base + cas * kChunkStride + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
                 for (int k = 0; k < kSums; ++k) {
                     const int ch = hsel + kSplit * k;
@@ -437,21 +438,11 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
             tc_fence_after();
         }
         const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(quad * 32) << 16);
-#ifdef BYOLO_DBG_HOOKS
-        if (!(p.dbg & 2))
-#endif
-#pragma unroll
-        for (int k = 0; k < (X3 ? kSums : 8); ++k) {
-            const int ch = hsel + kSplit * k;
-            if (ch >= nchunks) break;
+        // one column chunk of this row: accumulator values -> epilogue math -> store(s)
+        auto do_chunk = [&](const int ch, auto&& fetch) {
             const int c0 = ch * CH;                  // column inside the tile
             uint32_t raw[32];
-            if constexpr (X3) {
-#pragma unroll
-                for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(sums[k][j]);
-            } else {
-                if constexpr (kF32) tmem_ld16(taddr + c0, raw); else tmem_ld32(taddr + c0, raw);
-            }
+            fetch(raw, c0);
             uint4 rcur[NO] = {};
             if constexpr (kRes) {
                 if constexpr (X3) res_prefetch(tile, ch);        // split mode: the epilogue is off the critical path, load at use
@@ -531,6 +522,27 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
                     }
                 }
             }
+        };
+#ifdef BYOLO_DBG_HOOKS
+        if (!(p.dbg & 2))
+#endif
+        {
+            if constexpr (X3) {
+#pragma unroll
+                for (int k = 0; k < kSums; ++k) {
+                    const int ch = hsel + kSplit * k;
+                    if (ch < nchunks)
+                        do_chunk(ch, [&](uint32_t (&raw)[32], int) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(sums[k][j]);
+                        });
+                }
+            } else {
+                for (int ch = hsel; ch < nchunks; ch += kSplit)
+                    do_chunk(ch, [&](uint32_t (&raw)[32], int c0) {
+                        if constexpr (kF32) tmem_ld16(taddr + c0, raw); else tmem_ld32(taddr + c0, raw);
+                    });
+            }
         }
         if constexpr (!X3) {
             tc_fence_before();
@@ -582,7 +594,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             mbar_init(smem_u32(&ctl->full[s]), p.bsplit ? 2 : 1);       // split: the A and the B producer warp each post their byte count
             mbar_init(smem_u32(&ctl->empty[s]), 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 4; ++s) {
             mbar_init(smem_u32(&ctl->acc_full[s]), 1);
             mbar_init(smem_u32(&ctl->acc_empty[s]), EW * CG);      // CG = 2: both CTAs' epilogues release the leader
         }
@@ -762,10 +774,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             uint32_t chunk_it = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 for (int kb = 0; kb < num_kb; ++chunk_it) {
-                    const uint32_t as = chunk_it & 1, aphase = (chunk_it >> 1) & 1;
-                    mbar_wait(acc_empty0 + 8 * as, aphase ^ 1);
+                    const uint32_t as = chunk_it & 3, aphase = (chunk_it >> 2) & 1;      // four chunk buffers of 128 columns:
+                    mbar_wait(acc_empty0 + 8 * as, aphase ^ 1);                            // the issuer runs up to 3 chunks ahead of the drain
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + as * kAccStride;
+                    const uint32_t d_tmem = tmem_base + as * kChunkStride;
                     for (int cs = 0; cs < chunk_stages && kb < num_kb; ++cs, kb += kbs) {
                         const int nkb = min(kbs, num_kb - kb);
                         mbar_wait(full0 + 8 * stage, phase);
@@ -1106,6 +1118,7 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     const int stage_bytes = p.kbs * kb_bytes;
     BY_REQUIRE(budget / stage_bytes >= 2, "conv tile does not fit two pipeline stages in shared memory");
     p.chunk_stages = 1;                                           // split mode: 12 MMAs (8 cross terms, then 4 hi * hi) per accumulator chunk
+    if (dbg_env("BYOLO_CHUNK") > 0) p.chunk_stages = dbg_env("BYOLO_CHUNK");
     p.chunks_per_tile = ((num_kb + p.kbs - 1) / p.kbs + p.chunk_stages - 1) / p.chunk_stages;
     p.num_stages = std::min(kMaxStages, budget / stage_bytes);
     L->smem_bytes = p.num_stages * stage_bytes + 1024 + sizeof(SmemCtl) + p.epi_warps * kStageOutBytes + 64;

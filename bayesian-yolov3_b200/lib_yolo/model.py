@@ -31,15 +31,58 @@ class ModelBlueprint:
         self.cls_cnt = cls_cnt
 
 
+class _Activations:
+    """Lazy read-back of conv outputs of the most recent run (byolo_get_activation): nothing is copied off the device
+    unless a script actually looks at `raw_output`, `dn_out`, `det_net_*_out` or `layers[i]`."""
+
+    def __init__(self):
+        self.engine, self.run_id, self.cache = None, 0, {}
+
+    def bind(self, engine):
+        self.engine, self.run_id, self.cache = engine, self.run_id + 1, {}
+
+    def get(self, conv_index):
+        if self.engine is None:
+            return None                                           # no run yet (graph tensors have no value either)
+        if conv_index not in self.cache:
+            self.cache[conv_index] = self.engine.activation(conv_index).cpu().numpy()
+        return self.cache[conv_index]
+
+
+class _LayerList:
+    """`Model.layers`: the outputs of the 75 convolutions in creation (= weight file) order, read lazily.  The
+    reference's list (model.py:40-41) also holds the residual adds, routes and upsamplings; here the add is part of the
+    block-closing conv's output and routes / upsamplings are not materialised."""
+
+    def __init__(self, acts):
+        self._acts = acts
+
+    def __len__(self):
+        return 75
+
+    def __getitem__(self, i):
+        return self._acts.get(range(75)[i])
+
+
+DN_OUT_CONV = 51                       # darknet53 output (reference layer 74)
+DET_CONVS = (58, 66, 74)               # the three detection convs (raw head outputs)
+
+
 class DetLayer(DetLayerBlueprint):
     """One detection scale.  `bbox` (list of 3 per-prior arrays [..,g,g,D]), `raw_output` and `det` hold the values of
     the most recent run (None before the first run) - in the reference they are graph tensors."""
 
-    def __init__(self, input_img_size, downsample_factor, priors, layer_id):
+    def __init__(self, input_img_size, downsample_factor, priors, layer_id, acts=None):
         super().__init__(input_img_size, downsample_factor, priors)
         self.layer_id = layer_id
         self.loc_loss = self.obj_loss = self.cls_loss = None
-        self.bbox = self.raw_output = self.det = None
+        self.bbox = self.det = None
+        self._acts = acts
+
+    @property
+    def raw_output(self):
+        """Output of the detection conv (model.py:122,151,184): [B (or T), g, g, 3*(5+C) | 3*2*(5+C)] fp32."""
+        return self._acts.get(DET_CONVS[self.layer_id]) if self._acts is not None else None
 
     def matches_blueprint(self, bp):
         return (self.h, self.w, self.downsample, len(self.priors)) == (bp.h, bp.w, bp.downsample, len(bp.priors)) and all(
@@ -53,10 +96,16 @@ class Model:
         self.variant, self.inputs, self.cls_cnt = variant, inputs, cls_cnt
         self.obj_idx, self.cls_start_idx, self.T = obj_idx, cls_start_idx, T
         self.img_size = img_size
-        self.det_layers = [DetLayer(img_size, s, priors[s], i) for i, s in enumerate((32, 16, 8))]
-        self.layers = []                      # ModelBuilder's tensor list has no counterpart; see Engine.activation()
-        self.dn_out = self.det_net_1_out = self.det_net_2_out = self.det_net_3_out = None
+        self._acts = _Activations()
+        self.det_layers = [DetLayer(img_size, s, priors[s], i, self._acts) for i, s in enumerate((32, 16, 8))]
+        self.layers = _LayerList(self._acts)
         self._engine_factory, self._engine, self._max_batch = engine_factory, None, 0
+
+    # yolov3.py:306-310, 624-628: backbone output and the raw outputs of the three detection sub-nets
+    dn_out = property(lambda self: self._acts.get(DN_OUT_CONV))
+    det_net_1_out = property(lambda self: self._acts.get(DET_CONVS[0]))
+    det_net_2_out = property(lambda self: self._acts.get(DET_CONVS[1]))
+    det_net_3_out = property(lambda self: self._acts.get(DET_CONVS[2]))
 
     def matches_blueprint(self, blueprint):
         return self.cls_cnt == blueprint.cls_cnt and all(
@@ -81,6 +130,7 @@ class Model:
         boxes, cnt, idx, rows = eng.detect(torch.from_numpy(img).to(eng.device), seed=seed, image_index0=image_index0,
                                            max_out=max_out, want_rows=True)
         torch.cuda.synchronize(eng.device)
+        self._acts.bind(eng)
         res = dict(rows=rows.cpu().numpy(), boxes=boxes.cpu().numpy(), count=cnt.cpu().numpy(), idx=idx.cpu().numpy())
         off = 0
         for dl in self.det_layers:                              # per-prior views in the reference's shapes

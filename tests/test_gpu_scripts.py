@@ -83,3 +83,23 @@ def test_inference_aleatoric_script_batches(tmp_path):
         rec = json.load(open(os.path.join(out, 'img%d.json' % b)))['children']
         assert len(rec) == int(g['nms_count'][b])            # unequal counts per image are fine here (reference: SURVEY 3.4)
         assert abs(rec[0]['score'] - float(g['nms_rows'][b, 0, 9]) * float(g['nms_rows'][b, 0, 11:13].max())) < 1e-3
+
+
+def test_model_exposes_backbone_and_raw_head_outputs():
+    """Model.dn_out / det_net_{1,2,3}_out (yolov3.py:306-310) and DetLayer.raw_output (model.py:122) read back the values
+    of the last run, and equal what the reference's graph produced for the same inputs (fp32 path, 1e-3)."""
+    from byolo import compat as tf
+    from lib_yolo import yolov3
+    case, g = GI.CASES['aleatoric_128'], np.load(os.path.join(G, 'aleatoric_128.npz'))
+    cfg = {'full_img_size': list(case['img_size']), 'crop': False, 'cls_cnt': 2, 'priors': yolov3.ECP_9_PRIORS, 'aleatoric_loss': False,
+           'weights': W.synthetic('aleatoric', 2, case['weight_seed']), 'precision': 'fp32'}
+    img = tf.Placeholder((None,) + tuple(case['img_size']))
+    model = yolov3.yolov3_aleatoric(cfg).init_model(inputs=img, training=False).get_model()
+    assert model.dn_out is None and model.det_layers[0].raw_output is None          # nothing has run yet
+    model.execute(GI.images(case))
+    assert np.allclose(model.dn_out, g['dn_out'], rtol=1e-3, atol=1e-3)
+    for j, dl in enumerate(model.det_layers):
+        assert dl.raw_output.shape == g['raw%d' % j].shape
+        assert np.allclose(dl.raw_output, g['raw%d' % j], rtol=1e-3, atol=1e-3)
+        assert getattr(model, 'det_net_%d_out' % (j + 1)) is dl.raw_output            # same cached array
+    assert len(model.layers) == 75 and model.layers[51] is model.dn_out and model.layers[-1].shape[-1] == 42

@@ -768,7 +768,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
           } else {
             // Split mode.  The tensor core adds into its fp32 accumulator with TRUNCATION (measured, tools/x3_probe.py: a
             // signed bias of -2.8e-9 * K relative, -1.3e-5 for a 3x3x512 conv - it compounds over 75 layers), so an
-            // accumulator only ever takes one CHUNK of `chunk_stages` pipeline stages (12 MMAs); the epilogue warps drain
+            // accumulator only ever takes one CHUNK of `chunk_stages` pipeline stages (24 MMAs); the epilogue warps drain
             // each chunk into round-to-nearest fp32 register sums while the next chunk runs in the other accumulator.
             const int chunk_stages = p.chunk_stages;
             uint32_t chunk_it = 0;
@@ -1117,7 +1117,10 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     }
     const int stage_bytes = p.kbs * kb_bytes;
     BY_REQUIRE(budget / stage_bytes >= 2, "conv tile does not fit two pipeline stages in shared memory");
-    p.chunk_stages = 1;                                           // split mode: 12 MMAs (8 cross terms, then 4 hi * hi) per accumulator chunk
+    // split mode: 2 stages = 24 MMAs per accumulator chunk (per stage the 8 cross terms first, then the 4 hi * hi terms: 16
+    // adds land on a large accumulator).  One stage per chunk halves the truncation bias again but makes the kernel
+    // TMEM-read bound - every chunk is 64 KB of tcgen05.ld per CTA - 698 vs 787 img/s (profiles/r02/exp_x3_chunk.txt)
+    p.chunk_stages = 2;
     if (dbg_env("BYOLO_CHUNK") > 0) p.chunk_stages = dbg_env("BYOLO_CHUNK");
     p.chunks_per_tile = ((num_kb + p.kbs - 1) / p.kbs + p.chunk_stages - 1) / p.chunk_stages;
     p.num_stages = std::min(kMaxStages, budget / stage_bytes);

@@ -86,8 +86,9 @@ def test_split_fp16_tensor_core_path_within_1e3_of_the_oracle(name):
     assert not bad.any(), '%d/%d elements out of tolerance, per column %r' % (
         bad.sum(), bad.size, dict(zip(*np.unique(np.nonzero(bad)[-1], return_counts=True))))
     for a in agree:
-        # near-ties in the score order (1e-6 apart) may swap neighbours; the selected SET must agree
-        assert a['overlap'] >= 0.99 and a['same_rank'] >= 0.95, a
+        # values differ by ~1e-5, so a pair whose IoU sits within that of the 0.5 threshold (or two scores 1e-6 apart) can
+        # flip ONE decision, which then shifts every later rank: the selected SET must agree (>= 99 % index overlap)
+        assert a['overlap'] >= 0.99, a
 
 
 @pytest.mark.parametrize('name', list(CASES))

@@ -45,6 +45,7 @@ SIGNATURES = {
     'byolo_profile_read_coarse': (C.c_int, [_P, _P, _P, _P, _I]),
     'byolo_launch_count': (C.c_int, [_P, _I]),
     'byolo_flops_per_image': (C.c_double, [_P]),
+    'byolo_flops_per_image_executed': (C.c_double, [_P]),
 }
 
 _LIB = None

@@ -8,16 +8,17 @@ import numpy as np
 
 LABEL_TO_CLS_NAME = {1: 'pedestrian', 2: 'rider'}            # ECP; starts at 0 without implicit background class
 
-# (json key, column) tables; 'o+k' = obj_idx + k, 'c+k' = cls_start_idx + cls_cnt + k.
-# The aleatoric table reproduces the reference as written: its cls_entropy, layer_id and prior_id all read column
-# cls_start_idx + cls_cnt (inference_aleatoric.py:174-176); kept so files stay byte-compatible with the reference's.
+# (json key, column) tables in the reference's key order; 'o+k' = obj_idx + k, 'c+k' = cls_start_idx + cls_cnt + k, 'score' and
+# 'cls_scores' are the computed entries.  The aleatoric table reproduces the reference as written: its cls_entropy, layer_id
+# and prior_id all read column cls_start_idx + cls_cnt (inference_aleatoric.py:174-176).  Same keys, same order, same
+# values: json.dump writes the files byte for byte as the reference does.
 _COLUMNS = {
-    'standard': [],
-    'aleatoric': [('x_var', 4), ('y_var', 5), ('w_var', 6), ('h_var', 7), ('total_var', 8), ('obj_entropy', 'o+1'),
-                  ('cls_entropy', 'c+0'), ('layer_id', 'c+0'), ('prior_id', 'c+0')],
+    'standard': ['score', 'cls_scores'],
+    'aleatoric': [('x_var', 4), ('y_var', 5), ('w_var', 6), ('h_var', 7), ('total_var', 8), 'score', ('obj_entropy', 'o+1'),
+                  'cls_scores', ('cls_entropy', 'c+0'), ('layer_id', 'c+0'), ('prior_id', 'c+0')],
     'epistemic': [('x_var_epi', 4), ('y_var_epi', 5), ('w_var_epi', 6), ('h_var_epi', 7), ('x_var_ale', 8), ('y_var_ale', 9),
-                  ('w_var_ale', 10), ('h_var_ale', 11), ('total_var_epi', 12), ('total_var_ale', 13),
-                  ('obj_mutual_info', 'o+1'), ('obj_entropy', 'o+2'), ('ped_score', 17), ('rider_score', 18),
+                  ('w_var_ale', 10), ('h_var_ale', 11), ('total_var_epi', 12), ('total_var_ale', 13), 'score',
+                  ('obj_mutual_info', 'o+1'), ('obj_entropy', 'o+2'), 'cls_scores', ('ped_score', 17), ('rider_score', 18),
                   ('cls_mutual_info', 'c+0'), ('cls_entropy', 'c+1'), ('layer_id', 'c+2'), ('prior_id', 'c+3')],
 }
 
@@ -29,12 +30,16 @@ def bbox_to_ecp_format(variant, bbox, img_size, model, config):
     cls_idx = int(np.argmax(cls_scores))
     label = cls_idx + 1 if config['implicit_background_class'] else cls_idx
     rec = {'y0': float(bbox[0] * h), 'x0': float(bbox[1] * w), 'y1': float(bbox[2] * h), 'x1': float(bbox[3] * w)}
-    for key, col in _COLUMNS[variant]:
-        if isinstance(col, str):
-            col = (oi if col[0] == 'o' else cs + cc) + int(col[2:])
-        rec[key] = float(bbox[col])
-    rec['score'] = float(bbox[oi]) * float(bbox[cs + cls_idx])
-    rec['cls_scores'] = cls_scores
+    for entry in _COLUMNS[variant]:
+        if entry == 'score':
+            rec['score'] = float(bbox[oi]) * float(bbox[cs + cls_idx])
+        elif entry == 'cls_scores':
+            rec['cls_scores'] = cls_scores
+        else:
+            key, col = entry
+            if isinstance(col, str):
+                col = (oi if col[0] == 'o' else cs + cc) + int(col[2:])
+            rec[key] = float(bbox[col])
     rec['identity'] = LABEL_TO_CLS_NAME.get(label, label)
     return rec
 

@@ -169,8 +169,9 @@ class Engine:
     def launch_count(self, B):
         return _lib.check(self.lib.byolo_launch_count(self.h, B))
 
-    def flops_per_image(self):
-        return float(self.lib.byolo_flops_per_image(self.h))
+    def flops_per_image(self, executed=False):
+        """Algorithmic FLOPs of the reference graph per image, or (executed=True) what the tensor cores really run."""
+        return float((self.lib.byolo_flops_per_image_executed if executed else self.lib.byolo_flops_per_image)(self.h))
 
 
 def nms(rows, obj_idx, max_out=1000, iou_thr=0.5, packed=False, cluster=0, chunked=False):

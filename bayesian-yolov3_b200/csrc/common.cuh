@@ -107,6 +107,8 @@ struct ConvProblem {
     int c2;                  // channels of in2
     int t1, t2;              // MC stacking (layers.py:595-597) without a copy: sample s of the conv reads sample s / t1 of
                              // in1 (s / t2 of in2); 1 = the buffer holds every sample itself.  1x1 convs only.
+    int t_out;               // > 1 (tensor-core path only): gin.S counts IMAGES and every output row is stored t_out times, once per MC
+                             // sample with that sample's dropout mask - the conv over a stacked input without the T-fold GEMM
     int k, stride;           // 1|3, 1|2
     int cout_pad;            // rows of the weight matrix (multiple of 16)
     const __half* w16;       // [cout_pad, K] K-major, K = k*k*(C1+C2) ordered (tap, channel); BN scale folded

@@ -334,7 +334,8 @@ template <int CG, int EW, int KIND, bool X3>
 __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const UmmaParams& p, SmemCtl* ctl, uint32_t tmem_base,
                                              uint32_t out_stage, int warp, int lane, uint32_t rank, int first_tile, int tile_step) {
     constexpr bool kF32 = KIND == EPI_F32;
-    constexpr bool kDrop = KIND == EPI_F16_DROP;
+    constexpr bool kDropT = KIND == EPI_F16_DROP_T;     // T-invariant conv: one accumulator row -> T masked output samples
+    constexpr bool kDrop = KIND == EPI_F16_DROP || kDropT;
     constexpr bool kRes = KIND == EPI_F16_RES;
     constexpr bool kUp = KIND == EPI_UPSAMPLE;
     constexpr int CH = kF32 ? 16 : 32;
@@ -380,7 +381,12 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
         int us = 0, uy = 0, ux = 0;
         if constexpr (kDrop || kUp) {
             const uint32_t su = fdiv(row, p.fd_plane), rem = row - su * p.fd_plane.d;        // sample, pixel inside the map
-            if constexpr (kDrop) {
+            if constexpr (kDropT) {                  // GEMM rows run over the B images; t is the loop below
+                dr.image = (uint32_t)ep.drop.image0 + su;
+                dr.group0 = (rem * (uint32_t)ep.cout + (uint32_t)n0) >> 3;
+                us = (int)su;
+                ux = (int)rem;
+            } else if constexpr (kDrop) {
                 const uint32_t im = fdiv(su, p.fd_T);
                 dr.t = su - im * p.fd_T.d;
                 dr.image = (uint32_t)ep.drop.image0 + im;
@@ -466,10 +472,48 @@ __device__ __forceinline__ void run_epilogue(const CUtensorMap* map_o, const Umm
                     o4[j] = make_uint4(__float_as_uint(__uint_as_float(raw[4 * j]) + b.x), __float_as_uint(__uint_as_float(raw[4 * j + 1]) + b.y),
                                        __float_as_uint(__uint_as_float(raw[4 * j + 2]) + b.z), __float_as_uint(__uint_as_float(raw[4 * j + 3]) + b.w));
                 }
-            } else {
+            } else if constexpr (!kDropT) {
                 chunk_f16<kDrop, kRes, X3>(raw, ctl->bias + c, rcur, o4, ep.drop, dr, (uint32_t)c0 >> 3);
             }
-            if constexpr (!kUp) {
+            if constexpr (kDropT) {
+                // conv "75" (yolov3.py:538-544): its input is the MC-stacked backbone map, identical for the T samples of an
+                // image, so the GEMM ran once per image; here the same accumulator values get the T dropout masks and go to
+                // the T output samples: GEMM row (b, pixel) -> output rows ((b*T + t)*plane + pixel).  A warp's 32-row block
+                // that lies inside one image is 32 contiguous output rows (TMA store, as everywhere); the few blocks that
+                // run across an image boundary or past the last row are written with per-thread 16-byte stores.
+                const int plane = (int)p.fd_plane.d, T = (int)p.fd_T.d;
+                const int row0 = m_tile * kTileM + quad * 32;
+                const int b0 = (int)fdiv((uint32_t)row0, p.fd_plane), pix0 = row0 - b0 * plane;
+                const bool inside = pix0 + 32 <= plane && (uint32_t)(row0 + 32) <= out_rows;
+                __half* ob = reinterpret_cast<__half*>(ep.out);
+                for (int t = 0; t < T; ++t) {
+                    dr.t = (uint32_t)t;
+                    chunk_f16<true, false, X3>(raw, ctl->bias + c, rcur, o4, ep.drop, dr, (uint32_t)c0 >> 3);
+#pragma unroll
+                    for (int pl = 0; pl < NP; ++pl) {
+                        if (inside) {
+                            if (lane == 0) bulk_wait_read0();
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t dst = stg_row + (((uint32_t)j ^ swz) << 4);
+                                const uint4 v = o4[4 * pl + j];
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                            }
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(map_o, stg, pl * ldc + c, (b0 * T + t) * plane + pix0);
+                                bulk_commit();
+                            }
+                        } else if (valid) {
+                            uint4* dst = reinterpret_cast<uint4*>(ob + ((size_t)(us * T + t) * plane + ux) * pitch + pl * ldc + c);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dst[j] = o4[4 * pl + j];
+                        }
+                    }
+                }
+            } else if constexpr (!kUp) {
                 // the warp's 32 x 64 B block(s) -> 64B-swizzled staging -> TMA store (rows past the end are clipped by the unit)
                 // (split mode: hi then lo through the same block - its main loop is 3x longer, the epilogue has time to spare,
                 // and a second block would cost a pipeline stage)
@@ -866,6 +910,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_consta
             case EPI_F16: run_epilogue<CG, EW, EPI_F16, X3>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
             case EPI_F16_RES: run_epilogue<CG, EW, EPI_F16_RES, X3>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
             case EPI_F16_DROP: run_epilogue<CG, EW, EPI_F16_DROP, X3>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step); break;
+            case EPI_F16_DROP_T:
+                if constexpr (AM == A_TILED)
+                    run_epilogue<CG, EW, EPI_F16_DROP_T, X3>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
+                break;
             default:
                 if constexpr (CG == 1 && AM == A_TILED) {
                     if (p.epi_kind == EPI_F32) run_epilogue<CG, EW, EPI_F32, X3>(&map_o, p, ctl, tmem_base, out_stage, warp, lane, rank, first_tile, tile_step);
@@ -1016,6 +1064,9 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     BY_REQUIRE((t1 == 1 && t2 == 1) || q.k == 1, "MC-stacked sources only feed 1x1 convs");
     BY_REQUIRE(!(t1 > 1 && q.in2) && !(t2 > 1 && !q.in2), "stacked source: in1 alone, or in2 of a concat");
     BY_REQUIRE(g.S % t1 == 0 && g.S % t2 == 0, "sample count must be a multiple of the stacking factor");
+    const int t_out = std::max(q.t_out, 1);            // > 1: T-invariant conv, every GEMM row is stored as t_out masked samples
+    BY_REQUIRE(t_out == 1 || (q.k == 1 && !q.in2 && t1 == 1 && q.ep.drop.enabled && q.ep.drop.T == t_out && q.ep.out_mode == OUT_DENSE),
+               "t_out: plain 1x1 dropout conv over un-stacked images only");
     p.BK = (C1 % 64 == 0 && C2 % 64 == 0) ? 64 : 32;
     p.taps = q.k * q.k;
     p.kb1 = C1 / p.BK;
@@ -1073,11 +1124,11 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
     p.ep.drop.thr16 = std::min<uint32_t>(p.ep.drop.thr16, 65535u);
     if (q.ep.out_mode == OUT_DENSE_F32) p.epi_kind = EPI_F32;
     else if (q.ep.out_mode == OUT_UPSAMPLE2) p.epi_kind = EPI_UPSAMPLE;
-    else if (q.ep.drop.enabled) p.epi_kind = EPI_F16_DROP;
+    else if (q.ep.drop.enabled) p.epi_kind = t_out > 1 ? EPI_F16_DROP_T : EPI_F16_DROP;
     else if (q.ep.residual) p.epi_kind = EPI_F16_RES;
     else p.epi_kind = EPI_F16;
     BY_REQUIRE((p.epi_kind == EPI_F32) == !q.ep.leaky, "fp16 outputs are conv+BN+leaky layers, the fp32 output is the linear detection conv");
-    BY_REQUIRE(!(q.ep.drop.enabled && (q.ep.residual || p.epi_kind != EPI_F16_DROP)), "dropout only on plain convs");
+    BY_REQUIRE(!(q.ep.drop.enabled && (q.ep.residual || (p.epi_kind != EPI_F16_DROP && p.epi_kind != EPI_F16_DROP_T))), "dropout only on plain convs");
     BY_REQUIRE(!(q.ep.residual && p.epi_kind != EPI_F16_RES), "residual only on plain convs");
     BY_REQUIRE(!((p.epi_kind == EPI_F32 || p.epi_kind == EPI_UPSAMPLE) && p.amode != A_TILED), "detection / upsampling convs are plain 1x1 convs");
     p.fd_plane = make_fastdiv((uint32_t)(p.gout.H * p.gout.W));
@@ -1163,7 +1214,7 @@ int umma_prepare(const ConvProblem& q, UmmaLaunch* L) {
         // output map: [rows, ldc] of the dense output, 32 x 64 B boxes
         const bool f32 = p.epi_kind == EPI_F32;
         const uint64_t pitch = (uint64_t)q.ep.ldc * (f32 ? 1 : npl);
-        uint64_t d[2] = {pitch, (uint64_t)p.out_rows}, st[1] = {pitch * (f32 ? 4 : 2)};
+        uint64_t d[2] = {pitch, (uint64_t)p.out_rows * t_out}, st[1] = {pitch * (f32 ? 4 : 2)};      // t_out > 1: S * t_out output samples
         uint32_t box[2] = {(uint32_t)(f32 ? 16 : 32), 32u};
         if (int e = make_map(&L->o, q.ep.out, 2, d, st, box, one, 64, f32)) return e;
     }

@@ -10,7 +10,9 @@ enum EpiKind : int {
     EPI_F16_RES = 1,    //   ... + residual shortcut (layers.py:505-507)
     EPI_F16_DROP = 2,   //   dropout before the shift (layers.py:521-524, 560-570)
     EPI_F32 = 3,        // + bias, linear -> fp32 raw detection map, TMA store (layers.py:600-613)
-    EPI_UPSAMPLE = 4,   // shift + leaky -> fp16 stored to the four pixels of the nearest x2 upsample (layers.py:578-580)
+    EPI_UPSAMPLE = 4,
+    EPI_F16_DROP_T = 5, // T-invariant dropout conv (conv "75": input = MC-stacked backbone map, yolov3.py:538-544): the GEMM runs once
+                        // per IMAGE, the epilogue applies the T masks and stores the T samples (3D output map)   // shift + leaky -> fp16 stored to the four pixels of the nearest x2 upsample (layers.py:578-580)
 };
 
 // how the TMA producer fetches the A operand (activations)

@@ -215,6 +215,10 @@ static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int res
     const LayerDef& d = e->layers[li];
     const LayerWeights& w = e->weights[li];
     Buffer bin = pl->bufs[in1];
+    // T-invariant conv (conv "75", yolov3.py:538-544: a 1x1 dropout conv whose ONLY input is a stacked backbone map): on the
+    // tensor-core paths the GEMM runs once per image and the epilogue writes the T masked samples (EPI_F16_DROP_T)
+    int t_out = 1;
+    if (e->umma() && t1 > 1 && in2 < 0 && d.k == 1 && drop_id >= 0 && out_mode == OUT_DENSE) { t_out = t1; t1 = 1; }
     bin.g.S *= t1;                                  // geometry as the conv sees it
     BY_REQUIRE(bin.g.C + (in2 >= 0 ? pl->bufs[in2].g.C : 0) == d.cin, "plan wiring: channel mismatch");
     BY_REQUIRE(in2 < 0 || pl->bufs[in2].g.S * t2 == bin.g.S, "plan wiring: sample count mismatch");
@@ -226,7 +230,7 @@ static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int res
     } else if (out_mode == OUT_UPSAMPLE2) {
         if (int r = new_buffer(e, pl, bin.g.S, 2 * Ho, 2 * Wo, d.cout, false, &ob)) return r;
     } else {
-        if (int r = new_buffer(e, pl, bin.g.S, Ho, Wo, d.cout, false, &ob)) return r;
+        if (int r = new_buffer(e, pl, bin.g.S * t_out, Ho, Wo, d.cout, false, &ob)) return r;
     }
     Step st;
     st.kind = STEP_CONV;
@@ -239,6 +243,7 @@ static int add_conv(byolo_engine* e, Plan* pl, int li, int in1, int in2, int res
     p.c2 = in2 >= 0 ? pl->bufs[in2].g.C : 0;
     p.t1 = t1;
     p.t2 = t2;
+    p.t_out = t_out;
     p.k = d.k;
     p.stride = d.s;
     p.cout_pad = w.cout_pad;
@@ -778,7 +783,11 @@ int byolo_conv_layer(int32_t precision, const float* in1_dev, const float* in2_d
                   : launch_stem(in1_dev, S, H, W, w.w32, w.bias, po, half == ACT_F16, st);
     } else if (!rc) {
         ConvProblem p{};
-        p.in1 = p1; p.in2 = p2; p.gin = gc; p.c2 = cin2; p.k = k; p.stride = stride;
+        // a lone stacked input of a dropout conv takes the T-invariant route on the tensor-core paths, exactly as in the engine's plan
+        const bool tinv = umma && t1 > 1 && !in2_dev && k == 1 && dropout_layer >= 0 && !upsample && !dense;
+        p.in1 = p1; p.in2 = p2; p.gin = tinv ? g1 : gc; p.c2 = cin2; p.k = k; p.stride = stride;
+        p.t_out = tinv ? t1 : 1;
+        if (tinv) t1 = 1;
         p.cout_pad = w.cout_pad; p.w16 = w.w16; p.w32 = w.w32; p.x3 = x3;
         p.t1 = t1; p.t2 = t2;
         p.ep.bias = w.bias; p.ep.residual = pr; p.ep.out = po;
@@ -843,8 +852,12 @@ int byolo_launch_count(byolo_handle h, int32_t B) {
     return (int)pl->steps.size() + 2;      // + decode + nms
 }
 
-double byolo_flops_per_image(byolo_handle h) {
-    if (!h) return 0.0;
+static double flops_per_image(byolo_handle h, bool executed);
+
+double byolo_flops_per_image(byolo_handle h) { return h ? flops_per_image(h, false) : 0.0; }
+double byolo_flops_per_image_executed(byolo_handle h) { return h ? flops_per_image(h, true) : 0.0; }
+
+static double flops_per_image(byolo_handle h, bool executed) {
     double backbone = 0, head = 0;
     int Hc = h->cfg.height, Wc = h->cfg.width;
     // spatial size per layer follows the plan: backbone strides, head grids
@@ -857,11 +870,19 @@ double byolo_flops_per_image(byolo_handle h) {
         backbone += fl(h->layers[li++], Hc, Wc);
         for (int b = 0; b < 2 * blocks[s]; ++b) backbone += fl(h->layers[li++], Hc, Wc);
     }
+    double once = 0;        // executed only: conv "75" reads a T-invariant input, its GEMM runs once per image on the tensor-core paths
     for (int j = 0; j < 3; ++j) {
         if (j) head += fl(h->layers[li++], h->gh[j - 1], h->gw[j - 1]);
-        for (int i = 0; i < 7; ++i) head += fl(h->layers[li++], h->gh[j], h->gw[j]);
+        for (int i = 0; i < 7; ++i) {
+            const double f = fl(h->layers[li], h->gh[j], h->gw[j]);
+            const bool tinv = executed && j == 0 && i == 0 && h->mc() && h->umma() && h->cfg.T > 1 && h->layers[li].dropout &&
+                              !h->cfg.standard_test_dropout;
+            (tinv ? once : head) += f;
+            ++li;
+        }
     }
-    return backbone + head * (h->mc() ? h->cfg.T : 1);
+    // executed MMA work of the split mode: three tensor-core passes per product
+    return (backbone + once + head * (h->mc() ? h->cfg.T : 1)) * (executed && h->x3() ? 3.0 : 1.0);
 }
 
 }  // extern "C"

@@ -80,15 +80,27 @@ stem_mma_kernel(const float* __restrict__ img, int H, int W, int num_tiles, cons
     const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
     const int x0 = tx * kTW, y0 = ty * kTH;
     // stage the halo tile: rows y0-1 .. y0+16, columns (x0-1)*3 .. (x0+33)*3, zero outside the image (SAME padding)
-    for (int i = threadIdx.x; i < (kTH + 2) * kPitch; i += kWarps * 32) {
+    // all of a thread's loads are issued before the first conversion (one load in flight per thread left the kernel at
+    // 0.39 of the HBM rate: F2FP waiting on the scoreboard, profiles/r01/ncu_v7_single_stem.txt)
+    constexpr int kStageIters = ((kTH + 2) * kPitch + kWarps * 32 - 1) / (kWarps * 32);
+    float sv[kStageIters];
+#pragma unroll
+    for (int it = 0; it < kStageIters; ++it) {
+        const int i = threadIdx.x + it * kWarps * 32;
         const int r = i / kPitch, c = i - r * kPitch;
         const int iy = y0 - 1 + r, ix = x0 - 1 + c / 3;
-        float v = 0.f;
-        if (c < kInW && iy >= 0 && iy < H && ix >= 0 && ix < W)
-            v = __ldg(img + ((long long)(b * H + iy) * W + (x0 - 1)) * 3 + c);
-        const __half hi = __float2half_rn(v);
-        sin[0][i] = hi;
-        if constexpr (X3) sin[1][i] = __float2half_rn(v - __half2float(hi));
+        sv[it] = 0.f;
+        if (i < (kTH + 2) * kPitch && c < kInW && iy >= 0 && iy < H && ix >= 0 && ix < W)
+            sv[it] = __ldg(img + ((long long)(b * H + iy) * W + (x0 - 1)) * 3 + c);
+    }
+#pragma unroll
+    for (int it = 0; it < kStageIters; ++it) {
+        const int i = threadIdx.x + it * kWarps * 32;
+        if (i < (kTH + 2) * kPitch) {
+            const __half hi = __float2half_rn(sv[it]);
+            sin[0][i] = hi;
+            if constexpr (X3) sin[1][i] = __float2half_rn(sv[it] - __half2float(hi));
+        }
     }
     __syncthreads();
 

@@ -1,145 +1,7 @@
-"""Inference script for the yolov3.yolov3 class, same call surface as the reference's inference_standard_yolov3.py:
-Inference(yolo, config).run(), concat_bbox, nms, bbox_to_ecp_format, inference(config), main().  One JSON file per
-image in ECP format; the forward pass, decode and NMS run in libbyolo (sm_100a), not in a TensorFlow session.
-"""
-import json
-import logging
-import os
-import threading
-import time
+"""Same call surface as the reference's inference_standard_yolov3.py; the implementation is shared (byolo/inference_common.py)."""
+from byolo import inference_common as _common
 
-import numpy as np
-
-from byolo import compat as tf          # Session / errors.OutOfRangeError stand-ins
-from byolo import ecp
-from lib_yolo import dataset_utils, yolov3
-
-VARIANT = 'standard'
-
-
-class Inference:
-    def __init__(self, yolo, config):
-        self.batch_size = config['batch_size']
-        dataset = dataset_utils.TestingDataset(config)
-        self.img_tensor, self.filename_tensor = dataset.iterator.get_next()
-        weights, step = ecp.find_weights(config)
-        self.img_size = config['full_img_size']
-        assert not config['crop']
-        self.out_path = '{}_{}'.format(config['out_path'], step)
-        os.makedirs(self.out_path)
-        self.config = config
-        self.worker_thread = None
-        pass
-        yolo.load_weights(weights)
-        self.model = yolo.init_model(inputs=self.img_tensor, training=False).get_model()
-        bbox = concat_bbox([dl for dl in self.model.det_layers], model=self.model)
-        self.nms = nms(bbox, self.model)
-
-    def run(self):
-        with tf.Session(seed=self.config.get('seed', 0)) as sess:
-            self.sess = sess
-            step = 0
-            while True:
-                try:
-                    step += 1
-                    processed = self.process_batch(sess)
-                    if VARIANT != 'epistemic' or step % 15 == 0:
-                        logging.info('Processed {} images.'.format((step - 1) * self.batch_size + processed))
-                except tf.errors.OutOfRangeError:
-                    break
-            if self.worker_thread:
-                self.worker_thread.join()
-        return self
-
-    def process_batch(self, sess):
-        boxes, files = sess.run([self.nms, self.filename_tensor])
-        counts = sess.last_counts
-        if self.worker_thread:
-            self.worker_thread.join()
-        if VARIANT == 'epistemic':
-            boxes = boxes[None]                                   # [n,23] -> [1,n,23]
-            counts = [boxes.shape[1]]
-        # the arrays are caller-owned copies: the worker serialises them while the next batch runs
-        self.worker_thread = threading.Thread(target=self.write_to_disc, args=(boxes, files, counts))
-        self.worker_thread.start()
-        return len(files)
-
-    epistemic_forward_pass = process_batch                        # name used by inference_epistemic.py:75
-
-    def write_to_disc(self, all_boxes, files, counts):
-        for b, filename in enumerate(files):
-            self.write_ecp_json(all_boxes[b][:counts[b]], filename[0].decode('utf-8'))
-
-    def write_ecp_json(self, boxes, img_name):
-        return ecp.write_ecp_json(VARIANT, self.out_path, boxes, img_name, self.img_size, self.model, self.config)
-
-
-# -----------------------------------------------------------------#
-#                             helpers                              #
-# -----------------------------------------------------------------#
-
-def concat_bbox(net_out, model=None):
-    """Fetch handle for all candidate rows in (scale, prior, row, col) order.  net_out: the three detection layers (or
-    their .bbox lists, as the reference passes them); the rows are produced at their final offsets by the decode
-    kernel, so nothing is concatenated here."""
-    if model is None:
-        model = getattr(net_out[0], 'model', None)
-    assert model is not None, 'pass model= when handing over plain bbox lists'
-    return tf.RowsOp(model)
-
-
-def nms(boxes, model):
-    """Class-agnostic NMS (max 1000 boxes, IoU 0.5, no score threshold) + gather, as a fetch handle."""
-    return tf.NmsOp(boxes, model)
-
-
-def bbox_to_ecp_format(bbox, img_size, model, config):
-    return ecp.bbox_to_ecp_format(VARIANT, bbox, img_size, model, config)
-
-
-# -----------------------------------------------------------------#
-#                               main                               #
-# -----------------------------------------------------------------#
-
-def inference(config):
-    pass
-    assert not config['crop']
-    logging.info(json.dumps(config, indent=4, default=lambda x: str(x)))
-    logging.info('----- START -----')
-    start = time.time()
-    yolo = yolov3.yolov3(config)
-    Inference(yolo, config).run()
-    elapsed = int(time.time() - start)
-    logging.info('----- FINISHED in {:02d}:{:02d}:{:02d} -----'.format(elapsed // 3600, (elapsed // 60) % 60, elapsed % 60))
-
-
-def main():
-    config = {
-        'checkpoint_path': './checkpoints',  # edit
-        'run_id': 'yolov3',  # edit
-        'step': 'last',  # edit: int or 'last'
-        'full_img_size': [1024, 1920, 3],  # edit if not ECP dataset
-        'cls_cnt': 2,  # edit if not ECP dataset
-        'batch_size': 11,
-        'inference_mode': False,
-        'cpu_thread_cnt': 24,
-        'crop': False,
-        'training': False,
-        'aleatoric_loss': False,
-        'priors': yolov3.ECP_9_PRIORS,  # edit
-        'implicit_background_class': True,
-        'data': {
-            'path': '$HOME/data/ecp/images',  # edit: image files instead of the reference's tfrecords
-            'file_pattern': '*.png',  # edit
-        },
-    }
-    config['data']['file_pattern'] = os.path.join(os.path.expandvars(config['data']['path']), config['data']['file_pattern'])
-    config['out_path'] = os.path.join('./inference', config['run_id'])  # edit
-    inference(config)
-
+globals().update(_common.surface('standard'))
 
 if __name__ == '__main__':
-    np.set_printoptions(suppress=True, formatter={'float_kind': '{:5.3}'.format})
-    logging.basicConfig(level=logging.DEBUG, format='%(asctime)s, pid: %(process)d, %(levelname)-8s %(message)s',
-                        datefmt='%a, %d %b %Y %H:%M:%S')
-    main()
+    _common.run_as_script(main)  # noqa: F821

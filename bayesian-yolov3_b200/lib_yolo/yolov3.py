@@ -71,11 +71,19 @@ class _Base:
             self._model._engine.load_weights(self._resolve_weights())
 
     def load_darknet53_weights(self, weightfile):
-        """darknet.load_darknet_weights (darknet.py:42-122): backbone layers from a darknet53.conv.74-style file; the
-        head keeps whatever the current weights hold (synthetic seed 0 if none were given)."""
+        """darknet.load_darknet_weights (darknet.py:42-122): overwrites the 52 backbone convs from a darknet53.conv.74-style
+        file; the head keeps the weights that are configured (whatever form they were given in: layer list, BYW1 blob or
+        path, TF checkpoint, 'synthetic:<seed>').  Without configured weights the head is synthetic seed 0 - said aloud."""
         assert self._model is not None, 'Call init_model first.'
         table = _weights.layer_table(self.variant, self.cls_cnt)
-        base = self._weights if isinstance(self._weights, list) else _weights.synthetic(self.variant, self.cls_cnt, 0)
+        if self._weights is None and self._config.get('weights') is None:
+            import logging
+            logging.warning('load_darknet53_weights: no head weights configured, using synthetic(seed 0) for the head')
+            base = _weights.synthetic(self.variant, self.cls_cnt, 0)
+        else:
+            base = self._resolve_weights()
+            if isinstance(base, (bytes, bytearray)):
+                base = _weights.unpack(bytes(base))
         base = list(base)
         _weights.read_darknet(weightfile, table[:52], into=base)
         self.load_weights(base)

@@ -274,18 +274,25 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up: >= W steps AND >= warm_seconds of the same load (the power cap settles within ~0.1-1 s) ----
+    # Every rank must issue the SAME number of steps (each step carries a collective): rank 0 times a probe and broadcasts
+    # the count; nothing below depends on a per-rank clock.
+    for i in range(Wm):
+        step(i)
+    barrier()
     t_w0 = time.perf_counter()
-    n_warm = 0
-    while n_warm < Wm or (time.perf_counter() - t_w0) < args.warm_seconds:
-        step(n_warm)
-        n_warm += 1
-        if n_warm % 8 == 0:
+    for i in range(4):
+        step(i)
+    barrier()
+    per_step_s = max((time.perf_counter() - t_w0) / 4, 1e-5)
+    n_more = torch.tensor([int(min(max(args.warm_seconds, 0.0) / per_step_s, 20000))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(n_more, src=0)
+    n_more = int(n_more[0])
+    for i in range(n_more):
+        step(i)
+        if i % 8 == 7:
             torch.cuda.synchronize()
-    if world > 1:                                       # every rank runs the same number of collectives
-        t = torch.tensor([n_warm], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        for i in range(n_warm, int(t[0])):
-            step(i)
+    n_warm = Wm + 4 + n_more
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -448,7 +455,8 @@ def main():
                                              'meets the 1e-3 element-wise parity bound (tests/test_gpu_fullsize.py, profiles/r02/parity_*_fp16x3.txt)',
               'value': B * K / (ms3 * 1e-3), 'unit': 'images/s', 'ms_per_step': ms3 / K, 'steps': K,
               'e2e': {'value': B * K / (ms3_e2e * 1e-3), 'unit': 'images/s'},
-              'conv_stack_ms_per_step': stack3, 'gpu_launches': eng3.launch_count(B) * K}
+              'conv_stack_ms_per_step': stack3, 'gpu_launches': eng3.launch_count(B) * K,
+              'mma_factor': eng3.flops_per_image(executed=True) / eng3.flops_per_image()}
         eng3.close()
     if world > 1:
         t = torch.tensor([ms, ms_e2e, t_sus, ms_e2e_wall], device=dev)
@@ -493,7 +501,7 @@ def main():
                         break
                 except Exception:
                     pass
-            mma_factor = 3.0 if args.precision == 'fp16x3' else 1.0
+            mma_factor = eng.flops_per_image(executed=True) / eng.flops_per_image()
             res['roofline'] = {
                 'bound': 'tensor', 'kernel': 'conv_umma_kernel (all %d conv launches of a step)' % len(conv),
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
@@ -511,8 +519,8 @@ def main():
             if x3 is not None:
                 if x3['conv_stack_ms_per_step']:
                     alg = conv_fl / (x3['conv_stack_ms_per_step'] * 1e-3) / 1e12
-                    x3['roofline'] = {'bound': 'tensor', 'achieved': alg, 'executed': 3 * alg, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': alg / peak_tf,
-                                      'tensor_pipe_frac_executed': 3 * alg / peak_tf}
+                    x3['roofline'] = {'bound': 'tensor', 'achieved': alg, 'executed': x3['mma_factor'] * alg, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                                      'frac': alg / peak_tf, 'tensor_pipe_frac_executed': x3['mma_factor'] * alg / peak_tf}
                 res['parity_mode'] = x3
             big = [p for p in conv if p['ms'] > 0.3 and p['sm_mhz'] > 0]
             if big:      # effective SM clock inside the long conv launches (clock64/globaltimer): shows power-cap throttling

@@ -148,6 +148,10 @@ int byolo_launch_count(byolo_handle h, int32_t B);
 
 /* Algorithmic FLOPs (2*MAC over all 75 convs, backbone once + head x T) of one image, SURVEY.md 8d. */
 double byolo_flops_per_image(byolo_handle h);
+/* FLOPs the tensor cores actually execute per image: conv "75" of the Bayesian head reads the MC-stacked backbone map,
+ * identical for the T samples (yolov3.py:538-544), so its GEMM runs once per image (the T dropout masks are applied in the
+ * epilogue); BYOLO_PREC_FP16X3 executes three MMA passes per product. */
+double byolo_flops_per_image_executed(byolo_handle h);
 
 #ifdef __cplusplus
 }

@@ -351,3 +351,21 @@ def test_bench_reference_arm_prints_one_json_record():
         assert k in rec, k
     assert rec['impl'] == 'reference' and rec['value'] > 0 and rec['cpu_baseline']['kind'] == 'port' and rec['cpu_baseline']['cores'] >= 1
     assert rec['e2e']['h2d_bytes_per_step'] == 0 and 'workload' in rec['config'] and 'model' not in rec['config']
+
+
+def test_ecp_records_have_the_reference_keys_in_the_reference_order():
+    """bbox_to_ecp_format of the three inference scripts: same keys in the same order as the reference's dict literals
+    (tests/golden/ecp_keys.json, parsed from the reference sources by tests/golden/gen_ecp_keys.py), so json.dump writes
+    the files byte for byte like the reference."""
+    import json
+    from byolo import ecp
+    want = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'ecp_keys.json')))
+
+    class M:
+        pass
+    for variant, (oi, cs, D) in {'standard': (4, 5, 7), 'aleatoric': (9, 11, 16), 'epistemic': (14, 17, 23)}.items():
+        m = M()
+        m.obj_idx, m.cls_start_idx, m.cls_cnt = oi, cs, 2
+        rec = ecp.bbox_to_ecp_format(variant, np.arange(D, dtype=np.float32) / D, (608, 608, 3), m, {'implicit_background_class': True})
+        assert list(rec) == want[variant], variant
+        assert rec['identity'] == 'rider' and abs(rec['score'] - (oi / D) * ((cs + 1) / D)) < 1e-6

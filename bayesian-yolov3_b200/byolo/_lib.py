@@ -31,6 +31,7 @@ SIGNATURES = {
     'byolo_forward': (C.c_int, [_P, _P, _I, _U64, _I, _P, _P]),
     'byolo_nms': (C.c_int, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P]),
     'byolo_nms_ex': (C.c_int, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _I, _I, _I, _P]),
+    'byolo_class_filter': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'byolo_detect_packed': (C.c_int, [_P, _P, _I, _U64, _I, _F, _I, _P, _P, _P]),
     'byolo_detect': (C.c_int, [_P, _P, _I, _U64, _I, _F, _I, _P, _P, _P, _P, _P]),
     'byolo_detect_host': (C.c_int, [_P, _P, _I, _U64, _I, _F, _I, _P, _P, _P]),

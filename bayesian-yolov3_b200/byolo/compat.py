@@ -84,8 +84,8 @@ class NmsOp(Op):
     array when every image keeps the same number of boxes (tf.concat in its while_loop) - here images
     that keep fewer are zero padded and the true counts are on `Session.last_counts`."""
 
-    def __init__(self, rows_op, model):
-        self.rows_op, self.model = rows_op, model
+    def __init__(self, rows_op, model, per_class=False):
+        self.rows_op, self.model, self.per_class = rows_op, model, per_class
 
 
 class Session:
@@ -133,6 +133,18 @@ class Session:
             return f.source.last_files
         if isinstance(f, NmsOp):
             res = self._forward(f.model, feed, cache)
+            if f.per_class:        # optional variant of inference_epistemic.py:104-126: one NMS per class, concatenated
+                import torch
+                from . import engine as _engine
+                m = f.model
+                per = _engine.nms_per_class(torch.from_numpy(res['rows']).cuda(), m.obj_idx, m.cls_start_idx, m.cls_cnt)
+                self.last_counts = [len(p) for p in per]
+                if m.variant == 'epistemic':
+                    return per[0]
+                out = np.zeros((len(per), max(self.last_counts + [1]), res['rows'].shape[-1]), np.float32)
+                for b, p in enumerate(per):
+                    out[b, :len(p)] = p
+                return out
             self.last_counts = res['count']
             if f.model.variant == 'epistemic':
                 return res['boxes'][0, :res['count'][0]].copy()

@@ -188,6 +188,25 @@ def nms(rows, obj_idx, max_out=1000, iou_thr=0.5, packed=False, cluster=0, chunk
     return (boxes, idx) if packed else (boxes, cnt, idx)
 
 
+def nms_per_class(rows, obj_idx, cls_start_idx, cls_cnt, max_out=1000, iou_thr=0.5):
+    """The per-class NMS of the reference's commented variant (inference_epistemic.py:104-126): for each class, NMS over the
+    rows whose score of that class is strictly the largest, results concatenated class by class.  rows [B,N,D] fp32 cuda
+    -> list (per image) of numpy arrays [n_b, D], n_b <= cls_cnt * max_out."""
+    assert rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous() and rows.dim() == 3
+    B, N, D = rows.shape
+    tmp = torch.empty_like(rows)
+    per_image = [[] for _ in range(B)]
+    with torch.cuda.device(rows.device):
+        for cls in range(cls_cnt):
+            _lib.check(_lib.lib().byolo_class_filter(_ptr(rows), B, N, D, obj_idx, cls_start_idx, cls_cnt, cls, _ptr(tmp), _stream()))
+            boxes, cnt, _ = nms(tmp, obj_idx, max_out, iou_thr)
+            boxes, cnt = boxes.cpu().numpy(), cnt.cpu().numpy()
+            for b in range(B):
+                sel = boxes[b, :cnt[b]]
+                per_image[b].append(sel[sel[:, obj_idx] > -np.inf])       # neutral filler rows (score -inf) come last
+    return [np.concatenate(p) for p in per_image]
+
+
 def conv_layer(x, kernel, bn=None, bias=None, x2=None, residual=None, stride=1, upsample=False, precision='fp16',
                dropout_layer=-1, T=1, seed=0, image_index0=0, drop_prob=0.1, t1=1, t2=1):
     """Per-layer test hook (byolo_conv_layer): x [S,H,W,C1] (+ x2 [S,H,W,C2]) dense fp32 cuda; kernel HWIO numpy;

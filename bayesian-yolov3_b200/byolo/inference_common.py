@@ -42,7 +42,7 @@ def surface(variant):
             yolo.load_weights(weights)
             self.model = yolo.init_model(inputs=self.img_tensor, training=False).get_model()
             bbox = concat_bbox([dl for dl in self.model.det_layers], model=self.model)
-            self.nms = nms(bbox, self.model)
+            self.nms = nms(bbox, self.model, per_class=config.get('per_class_nms', False))
 
         def run(self):
             with tf.Session(seed=self.config.get('seed', 0)) as sess:
@@ -91,9 +91,11 @@ def surface(variant):
         assert model is not None, 'pass model= when handing over plain bbox lists'
         return tf.RowsOp(model)
 
-    def nms(boxes, model):
-        """Class-agnostic NMS (max 1000 boxes, IoU 0.5, no score threshold) + gather, as a fetch handle."""
-        return tf.NmsOp(boxes, model)
+    def nms(boxes, model, per_class=False):
+        """Class-agnostic NMS (max 1000 boxes, IoU 0.5, no score threshold) + gather, as a fetch handle.  per_class=True
+        (config['per_class_nms']): the reference's commented variant "used to produce the results for the paper"
+        (inference_epistemic.py:104-126): one NMS per class over the rows where that class scores highest, concatenated."""
+        return tf.NmsOp(boxes, model, per_class=per_class)
 
     def bbox_to_ecp_format(bbox, img_size, model, config):
         return ecp.bbox_to_ecp_format(variant, bbox, img_size, model, config)

@@ -149,5 +149,7 @@ struct NmsOptions {
 };
 int launch_nms(const float* rows, int B, int N, int D, int obj_idx, float iou_thr, int max_out, float* out_rows,
                int* out_idx, int* out_count, const NmsOptions& opt, cudaStream_t st);  // nms.cu
+int launch_class_filter(const float* rows, long long total_rows, int D, int obj_idx, int cls_start, int cls_cnt, int cls, float* out,
+                        cudaStream_t st);                                      // nms.cu
 
 }  // namespace byolo

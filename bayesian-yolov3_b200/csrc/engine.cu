@@ -541,6 +541,12 @@ int byolo_nms_ex(const float* rows_dev, int32_t B, int32_t N, int32_t D, int32_t
     return launch_nms(rows_dev, B, N, D, obj_idx, iou_thr, max_out, out_rows_dev, out_idx_dev, out_count_dev, opt, (cudaStream_t)stream);
 }
 
+int byolo_class_filter(const float* rows_dev, int32_t B, int32_t N, int32_t D, int32_t obj_idx, int32_t cls_start_idx, int32_t cls_cnt,
+                       int32_t cls, float* out_rows_dev, void* stream) {
+    BY_REQUIRE(rows_dev && out_rows_dev && B >= 0 && N >= 0, "bad argument");
+    return launch_class_filter(rows_dev, (long long)B * N, D, obj_idx, cls_start_idx, cls_cnt, cls, out_rows_dev, (cudaStream_t)stream);
+}
+
 static int detect_impl(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,
                        int32_t max_out, float* rows_dev, float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev,
                        bool packed, void* stream) {

@@ -563,6 +563,37 @@ nms_chunked_kernel(const float* __restrict__ rows_all, int N, int D, int obj_idx
     if (CS > 1) cluster.sync();
 }
 
+// Per-class NMS support (the variant "used to produce the results for the paper", inference_epistemic.py:104-126: one NMS per
+// class over the rows whose score of that class is strictly greater than every other class score).  A copy of the rows in
+// which every OTHER row is neutralised - score -inf (sorts last) and a zero-area box (IoU 0 with everything, so it neither
+// suppresses nor gets suppressed) - makes the class-agnostic kernel select exactly the subset's boxes first.
+__global__ void class_filter_kernel(const float* __restrict__ rows, float* __restrict__ out, long long total, int D, int obj_idx,
+                                    int cls_start, int cls_cnt, int cls) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= total) return;
+    const float* src = rows + r * D;
+    float* dst = out + r * D;
+    const float mine = src[cls_start + cls];
+    bool keep = true;
+    for (int c = 0; c < cls_cnt; ++c)
+        if (c != cls && !(mine > src[cls_start + c])) keep = false;      // tf.greater: strict, ties belong to no class
+    for (int c = 0; c < D; ++c) dst[c] = src[c];
+    if (!keep) {
+        dst[0] = dst[1] = dst[2] = dst[3] = 0.f;
+        dst[obj_idx] = __int_as_float(0xff800000);
+    }
+}
+
+int launch_class_filter(const float* rows, long long total_rows, int D, int obj_idx, int cls_start, int cls_cnt, int cls, float* out,
+                        cudaStream_t st) {
+    BY_REQUIRE(obj_idx >= 4 && obj_idx < D && cls_start >= 4 && cls_cnt >= 1 && cls_start + cls_cnt <= D && cls >= 0 && cls < cls_cnt,
+               "class filter: column indices out of range");
+    if (total_rows == 0) return 0;
+    class_filter_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(rows, out, total_rows, D, obj_idx, cls_start, cls_cnt, cls);
+    BY_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_nms(const float* rows, int B, int N, int D, int obj_idx, float iou_thr, int max_out, float* out_rows, int* out_idx,
                int* out_count, const NmsOptions& opt, cudaStream_t st) {
     BY_REQUIRE(N >= 0 && (long long)N * D < (1ll << 31), "NMS: candidate rows must be 32-bit indexable");

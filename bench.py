@@ -114,11 +114,12 @@ class CpuReference:
     for the stress configuration.  Model construction (weight synthesis, kernel layout) happens ONCE, here; run() is what
     gets timed.  torchrun exports OMP_NUM_THREADS=1: the thread count is set explicitly to all cores of the box."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, reserve=0):
         import torch
         from byolo import priors as P, weights as W
         from oracle import net as ON
-        self.cfg, self.threads = cfg, host_threads()
+        # reserve: cores left to the other ranks of a multi-GPU run, which spin in the closing barrier meanwhile
+        self.cfg, self.threads = cfg, max(1, host_threads() - reserve)
         torch.set_num_threads(self.threads)
         self.pri = P.as_scale_list(P.by_stride('ECP_9_PRIORS'))
         v = cfg['variant']
@@ -539,8 +540,10 @@ def main():
                                       'around each launch, L2 flushed before); the kernel is latency bound (sort + sequential greedy scan), not byte bound',
                                'nms_ms_per_launch': nms_ms}
         if not args.no_cpu_baseline:
-            ref = CpuReference(cfg)
+            ref = CpuReference(cfg, reserve=world - 1)
             n_cpu = 256 if stress else (8 if T >= 10 else 16)      # ~5-20 s of CPU work
+            if world > 1 and not stress:
+                n_cpu = 4                                           # the other ranks wait (busy) in the closing barrier
             ref.run(1)
             t0 = time.perf_counter()
             ref.run(n_cpu)

@@ -83,6 +83,13 @@ int byolo_nms_ex(const float* rows_dev, int32_t B, int32_t N, int32_t D, int32_t
                  float* out_rows_dev, int32_t* out_idx_dev, int32_t* out_count_dev, int32_t packed, int32_t force_cluster_size,
                  int32_t force_chunked, void* stream);
 
+/* Per-class NMS (the commented variant of inference_epistemic.py:104-126, "used to produce the results for the paper"): copies
+ * rows_dev [B,N,D] to out_rows_dev with every row whose class `cls` score is NOT strictly greater than all other class scores
+ * neutralised (score -inf, zero-area box).  byolo_nms on the copy then selects exactly what NMS over the class's subset
+ * selects, followed - only if fewer than max_out of them survive - by neutral rows (score -inf), which the caller drops. */
+int byolo_class_filter(const float* rows_dev, int32_t B, int32_t N, int32_t D, int32_t obj_idx, int32_t cls_start_idx, int32_t cls_cnt,
+                       int32_t cls, float* out_rows_dev, void* stream);
+
 /* forward + nms on device buffers (what Inference.nms fetches, inference_epistemic.py:50-54). rows_dev may be NULL
  * (internal scratch is used). */
 int byolo_detect(byolo_handle h, const float* img_dev, int32_t B, uint64_t seed, int32_t image_index0, float iou_thr,

@@ -86,6 +86,26 @@ def test_nms_packed_output_carries_the_count_row():
     assert packed[2, 1000, 0] == 1
 
 
+def test_nms_per_class_matches_the_reference_variant():
+    """inference_epistemic.py:104-126 (commented, "used to produce the results for the paper"): per class, rows whose class
+    score is strictly greater than the other's -> NMS(1000) -> concatenated.  Bit exact vs the oracle NMS on the subsets."""
+    import byolo
+    rows = stress_rows(2, 108)
+    rows[:, :, 17:19] = np.random.default_rng(9).random((2, rows.shape[1], 2), dtype=np.float32)     # class scores
+    rows[0, :50, 18] = rows[0, :50, 17]                          # exact class ties belong to no class (tf.greater)
+    rows[1, 2000:, 17] = 0.9                                     # image 1: few riders -> fewer than 1000 survive
+    rows[1, 2000:, 18] = 0.1
+    got = byolo.nms_per_class(torch.from_numpy(rows).cuda(), 14, 17, 2)
+    for b in range(2):
+        want = []
+        for cls in (0, 1):
+            sub = rows[b][rows[b][:, 17 + cls] > rows[b][:, 18 - cls]]
+            want.append(sub[ONMS.nms(sub, 14)])
+        want = np.concatenate(want)
+        assert got[b].shape == want.shape and np.array_equal(got[b], want), (b, got[b].shape, want.shape)
+    assert len(got[1]) < 2000
+
+
 def _random_rows(B, N, D, obj_idx, seed, tie_frac=0.05):
     rng = np.random.default_rng(seed)
     rows = rng.random((B, N, D), dtype=np.float32)

@@ -141,8 +141,12 @@ def _snappy_decompress(src):
             pos += 4
         if off == 0 or off > len(out):
             raise ValueError('corrupt snappy stream')
-        for _ in range(ln):                              # copies may overlap their own output
-            out.append(out[-off])
+        if off >= ln:                                    # plain back-reference: one slice
+            start = len(out) - off
+            out += out[start:start + ln]
+        else:                                            # overlapping copy = the last `off` bytes repeated
+            pat = bytes(out[-off:])
+            out += (pat * (ln // off + 1))[:ln]
     if len(out) != n:
         raise ValueError('corrupt snappy stream (length)')
     return bytes(out)
@@ -266,7 +270,12 @@ def read_bundle(prefix, names=None):
 def load(prefix, variant, cls_cnt=2):
     """checkpoint prefix -> byolo.weights layer list (what Engine.load_weights takes)."""
     wanted = {n for n, _ in variable_names(variant, cls_cnt)}
-    return weights_from_variables(variant, cls_cnt, read_bundle(prefix, wanted))
+    variables = read_bundle(prefix, wanted)
+    missing = sorted(n for n in wanted if n not in variables and n + ':0' not in variables)
+    if missing:          # a checkpoint of another model class / cls_cnt must not fall through to a half-initialised engine
+        raise KeyError('checkpoint %s lacks %d of the %d variables of the %s model (cls_cnt %d): %s%s' % (
+            prefix, len(missing), len(wanted), variant, cls_cnt, ', '.join(missing[:8]), ' ...' if len(missing) > 8 else ''))
+    return weights_from_variables(variant, cls_cnt, variables)
 
 
 def latest_checkpoint(directory):

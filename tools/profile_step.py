@@ -11,7 +11,7 @@ import byolo  # noqa: E402
 from byolo import weights as W  # noqa: E402
 
 B = int(os.environ.get('PROF_B', '16'))
-eng = byolo.Engine('epistemic', (608, 608), 2, T=10, max_batch=B, precision='fp16').load_weights(W.synthetic('epistemic', 2, 0))
+eng = byolo.Engine('epistemic', (608, 608), 2, T=10, max_batch=B, precision=os.environ.get('PROF_PRECISION', 'fp16')).load_weights(W.synthetic('epistemic', 2, 0))
 img = torch.from_numpy(np.random.default_rng(1).random((B, 608, 608, 3), dtype=np.float32)).cuda()
 for _ in range(2):
     eng.detect(img, seed=1003)

@@ -31,7 +31,11 @@ def box_op_bayes(model):
 
 
 def filter_boxes(boxes, obj_idx, thresh):
-    return [box for box in boxes if box[obj_idx] > thresh]
+    """Rows whose objectness exceeds `thresh` (detect.py:36-37), as a list of rows like the reference returns."""
+    boxes = np.asarray(boxes)
+    if boxes.size == 0:
+        return []
+    return list(boxes[boxes[:, obj_idx] > thresh])
 
 
 def preproces_boxes(img_size, boxes, obj_idx, cls_start_idx, cls_cnt, config, cls_mapping=None):
@@ -51,12 +55,20 @@ def preproces_boxes(img_size, boxes, obj_idx, cls_start_idx, cls_cnt, config, cl
 
 
 def draw_boxes(img, boxes, color=(43, 219, 216), thickness=1):
+    """Overlay of label, score and rectangle on a float RGB image in [0,1] (out of the hot path; same signature and look
+    as the reference helper, detect.py:66-73)."""
     import cv2
-    color = np.array(color) / 255.
-    for box in boxes:
-        text = '{} {:4.3f}'.format(box['cls'], box['score'])
-        cv2.putText(img, text, (int(box['x0']), int(box['y0'])), cv2.FONT_HERSHEY_SIMPLEX, 0.5, color, thickness)
-        cv2.rectangle(img, (int(box['x0']), int(box['y0'])), (int(box['x1']), int(box['y1'])), color, thickness)
+    rgb = tuple(float(c) / 255.0 for c in color)
+    for b in boxes:
+        top_left, bottom_right = (int(b['x0']), int(b['y0'])), (int(b['x1']), int(b['y1']))
+        cv2.rectangle(img, top_left, bottom_right, rgb, thickness)
+        cv2.putText(img, '%s %4.3f' % (b['cls'], b['score']), top_left, cv2.FONT_HERSHEY_SIMPLEX, 0.5, rgb, thickness)
+
+
+def _centre_crop(img, size_hw):
+    """The window of size_hw around the image centre (what detect.py:79-82 cuts out when config['crop'] is set)."""
+    off = [(full - want) // 2 for full, want in zip(img.shape[:2], size_hw[:2])]
+    return img[off[0]:off[0] + size_hw[0], off[1]:off[1] + size_hw[1]]
 
 
 def load_img(config, img_size, filename):
@@ -67,10 +79,8 @@ def load_img(config, img_size, filename):
         import cv2
         img = cv2.imread(filename, cv2.IMREAD_COLOR)[:, :, ::-1].astype(np.float32) / np.float32(255.0)
     if config['crop']:
-        y = (img.shape[0] - img_size[0]) // 2
-        x = (img.shape[1] - img_size[1]) // 2
-        img = img[y:y + img_size[0], x:x + img_size[1], :]
-    return np.expand_dims(np.ascontiguousarray(img), axis=0)
+        img = _centre_crop(img, img_size)
+    return np.ascontiguousarray(img)[None]
 
 
 def load_model(sess, config, model_cls):

@@ -369,3 +369,37 @@ def test_ecp_records_have_the_reference_keys_in_the_reference_order():
         rec = ecp.bbox_to_ecp_format(variant, np.arange(D, dtype=np.float32) / D, (608, 608, 3), m, {'implicit_background_class': True})
         assert list(rec) == want[variant], variant
         assert rec['identity'] == 'rider' and abs(rec['score'] - (oi / D) * ((cs + 1) / D)) < 1e-6
+
+
+def test_gathered_views_even_and_uneven_shards():
+    """byolo.dist.Gathered: the receive buffer [world, per, max_out+1, D] as boxes / counts in global image order; even
+    shards are pure views of the buffer, uneven shards drop the padding images of the short ranks."""
+    from byolo import dist as bd
+    world, per, max_out, D = 3, 2, 4, 5
+    recv = torch.arange(world * per * (max_out + 1) * D, dtype=torch.float32).view(world, per, max_out + 1, D)
+    even = bd.Gathered(recv, world * per, world, max_out)
+    assert even.boxes.shape == (6, max_out, D) and even.counts.shape == (6,)
+    assert even.boxes.data_ptr() == recv.data_ptr()                         # a view, not a copy
+    assert torch.equal(even.boxes[3], recv[1, 1, :max_out]) and even.counts[3] == recv[1, 1, max_out, 0]
+    uneven = bd.Gathered(recv, 5, world, max_out)                           # shards 2, 2, 1
+    assert uneven.boxes.shape == (5, max_out, D)
+    assert torch.equal(uneven.boxes[4], recv[2, 0, :max_out]) and torch.equal(uneven.boxes[3], recv[1, 1, :max_out])
+    assert [bd.shard_range(5, r, 3) for r in range(3)] == [(0, 2), (2, 4), (4, 5)]
+
+
+def test_bench_arms_share_one_config_dict():
+    """The reference arm and the B200 arm of bench.py must print the same `config` (the driver compares them) and the
+    default configuration is the one BASELINE.json quotes the metric on (configs[2])."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    base = json.load(open(os.path.join(ROOT, 'BASELINE.json')))
+    assert sorted(bench.CONFIGS) == [1, 2, 3, 4, 5] and len(base['configs']) == 5
+    c3 = bench.CONFIGS[3]
+    assert (c3['variant'], c3['T'], c3['batch_per_gpu'], c3['img']) == ('epistemic', 10, 16, 608)
+    assert (bench.CONFIGS[4]['T'], bench.CONFIGS[4]['img'], bench.CONFIGS[4]['batch_per_gpu']) == (30, 416, 4)
+    assert bench.CONFIGS[5]['variant'] == 'nms-stress' and bench.CONFIGS[5]['batch_per_gpu'] == 8
+    for n, c in bench.CONFIGS.items():
+        assert c['workload'].startswith('configs[%d]' % (n - 1)) and 'model' not in c

@@ -74,7 +74,8 @@ class Forward:
         assert len(weights) == len(self.specs)
         self.weights = weights
         self.dtype = dtype
-        self.emulate = emulate          # None | 'half' | 'bf16': round conv operands like the GPU kernel does
+        self.emulate = emulate          # None | 'half' | 'bf16' | 'split': round conv operands like the GPU kernel does
+        #                                 ('split' = the fp16x3 mode: every operand a hi + lo fp16 pair, 22 significant bits)
         self.keep_layers = keep_layers
         self._folded = {}
 
@@ -84,6 +85,9 @@ class Forward:
             return x.to(torch.float16).to(self.dtype)
         if self.emulate == 'bf16':
             return x.to(torch.bfloat16).to(self.dtype)
+        if self.emulate == 'split':
+            hi = x.to(torch.float16).to(self.dtype)
+            return hi + (x - hi).to(torch.float16).to(self.dtype)
         return x
 
     def _kernel(self, idx):

@@ -179,3 +179,29 @@ def test_epistemic_determinant_column_against_float64():
     scale = np.prod(np.abs(rows64[:, 4:8]), -1)
     assert np.all(np.abs(rows32[:, 12] - rows64[:, 12]) <= 1e-3 * scale + 1e-12)
     assert np.allclose(rows32[:, 4:8], rows64[:, 4:8], rtol=1e-3, atol=1e-6)          # the diagonal itself
+
+
+def test_split_fp16_operands_carry_fp32_grade_precision():
+    """The arithmetic model of the tensor-core split mode (precision='fp16x3'): operands rounded to hi + lo fp16 pairs.
+    On the golden cases the rows stay within 1e-3 (+ floors) of the reference graph in EVERY element, while plain fp16
+    operands leave it - the reason the mode exists.  (The accumulation order of the device - chunked
+    round-to-nearest sums - is measured on the GPU, tests/test_gpu_fullsize.py.)"""
+    import parity_report as PR
+    for name in ('aleatoric_128', 'epistemic_96x160'):
+        case, g = GI.CASES[name], np.load(os.path.join(G, name + '.npz'))
+        w = W.synthetic(case['variant'], case['cls_cnt'], case['weight_seed'])
+        out = {}
+        for mode in ('split', 'half'):
+            res = ON.Forward(case['variant'], w, case['cls_cnt'], torch.float32, emulate=mode).run(
+                GI.images(case), T=case.get('T'), seed=case.get('dropout_seed', 0))
+            out[mode] = (np.stack([D.rows_from_raw('epistemic', r['raw'], PRI) for r in res]) if case['variant'] == 'epistemic'
+                         else D.rows_from_raw(case['variant'], res[0]['raw'], PRI))
+        assert not (PR.excess(out['split'], g['rows'], case['variant']) > 0).any(), name
+        assert (PR.excess(out['half'], g['rows'], case['variant']) > 0).mean() > 0.01, name
+    # the pair itself: 22 significant bits while lo is a normal fp16 number (|x| >= 2^-3), an absolute error <= 2^-25 below
+    # that (lo subnormal: the unbiased noise floor measured in profiles/r02/x3_probe_accumulator_truncation.txt)
+    split_err = lambda v: (v.half().float() + (v - v.half().float()).half().float() - v).abs()
+    big = (1 + torch.rand(1 << 16)) * torch.exp2(torch.randint(-3, 10, (1 << 16,)).float())
+    assert float((split_err(big) / big).max()) <= 2.0 ** -21
+    small = torch.rand(1 << 16) * 2.0 ** -3
+    assert float(split_err(small).max()) <= 2.0 ** -25

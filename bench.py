@@ -472,6 +472,9 @@ def main():
                'dtype': 'f32 (IoU compares)' if stress else dtype, 'data': 'synthetic', 'config': cfg,
                'precision': None if stress else args.precision, 'l2': l2_note,
                'warmup_steps_run': n_warm, 'warmup_seconds': args.warm_seconds,
+               'timing_note': 'K steps timed with CUDA events after >= %.1f s of the same load: the power cap (sw_power_cap, ~1000 W) has pulled the SM '
+                              'clock to its sustained level by then; round-1 lines were timed 5 steps after a cold start (boost clock) and read '
+                              '~7 %% higher for the same kernels' % args.warm_seconds,
                'p50_ms_per_img': ms / K / B, 'ms_per_step_with_per_launch_events': (ms_prof / K) if ms_prof else None,
                'sustained': ({'value': world * B * n_sus / (t_sus * 1e-3), 'unit': 'images/s', 'steps': n_sus, 'seconds': t_sus * 1e-3}
                              if n_sus else None),
